@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference (utils/homophily_metrics.py, utils/util_funcs.py) is imported
+from /root/reference as-is.  Its hard dependencies that are absent from this
+image and are NOT on the graph-statistics path (torch_scatter.scatter_add,
+dgl, torch_geometric, ogb, google_drive_downloader) are replaced by tiny stub
+modules so that the import succeeds; `scatter_add` is the only stub that is
+ever called and it forwards to torch's own Tensor.scatter_add_.
+
+Every fixture stores the inputs (`in_*`) handed to the reference functions and
+the outputs (`out_*`) those functions returned, so tests can replay the same
+inputs through oracle/ (CPU, `-m "not gpu"`) and through the CUDA path
+(`-m gpu`) without the reference being present.
+"""
+import os
+import random
+import sys
+import types
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+# --------------------------------------------------------------------------
+# stubs for dependencies that are not installed (none is on the hot path)
+# --------------------------------------------------------------------------
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _scatter_add(src, index, dim=-1, out=None, dim_size=None):
+    assert out is not None
+    return out.scatter_add_(dim, index, src)
+
+
+_stub("torch_scatter", scatter_add=_scatter_add)
+_stub("dgl")
+_tg = _stub("torch_geometric")
+_tg.utils = _stub("torch_geometric.utils", to_undirected=None)
+_stub("google_drive_downloader", GoogleDriveDownloader=object)
+_stub("ogb")
+_stub("ogb.nodeproppred", NodePropPredDataset=object)
+
+sys.path.insert(0, REF)
+_cwd = os.getcwd()
+os.chdir(REF)  # the reference opens "data/ind.cora.x" relative to its root
+import utils.homophily_metrics as hm  # noqa: E402
+import utils.util_funcs as uf  # noqa: E402
+
+
+def seed_all(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def t2n(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def try_call(fn):
+    """Return (value, '') or (nan, ExceptionTypeName)."""
+    try:
+        return fn(), ""
+    except Exception as e:  # the reference's own error behaviour is part of the contract
+        return None, type(e).__name__
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def coo_from_edges(row, col, n, vals=None):
+    idx = torch.from_numpy(np.vstack([row, col]).astype(np.int64))
+    v = torch.ones(idx.shape[1]) if vals is None else torch.from_numpy(vals.astype(np.float32))
+    return torch.sparse_coo_tensor(idx, v, (n, n)).coalesce()
+
+
+# --------------------------------------------------------------------------
+# the label/structure metrics (homophily_metrics.py) on one sparse adjacency
+# --------------------------------------------------------------------------
+def structure_metrics(adj, labels, out, onehot=True):
+    """adj: coalesced torch sparse COO (values irrelevant); labels: 1-D long."""
+    c = int(labels.max()) + 1
+    ei = adj.coalesce().indices()
+    v, e = try_call(lambda: hm.edge_homophily(adj, labels))
+    out["out_edge_homo"], out["err_edge_homo"] = (t2n(v) if e == "" else np.nan), e
+    if onehot:
+        oh = torch.eye(c)[labels.clamp(min=0)]
+        out["out_edge_homo_onehot"] = t2n(hm.edge_homophily(adj, oh))
+    v, e = try_call(lambda: hm.edge_homophily(adj, labels.numpy(), ignore_negative=True))
+    out["out_edge_homo_ignore_negative"], out["err_edge_homo_ignore_negative"] = (
+        (np.float64(v) if e == "" else np.nan), e)
+    v, e = try_call(lambda: hm.node_homophily(adj, labels))
+    out["out_node_homo"], out["err_node_homo"] = (t2n(v) if e == "" else np.nan), e
+    v, e = try_call(lambda: hm.compact_matrix_edge_idx(ei, labels))
+    out["out_compat"], out["err_compat"] = (t2n(v) if e == "" else np.zeros((c, c)) * np.nan), e
+    v, e = try_call(lambda: hm.our_measure(ei, labels))
+    out["out_class_homo"], out["err_class_homo"] = (t2n(v) if e == "" else np.nan), e
+    v, e = try_call(lambda: hm.class_distribution(adj, labels))
+    if e == "":
+        out["out_p"], out["out_p_bar"], out["out_pc"] = t2n(v[0]), t2n(v[1]), t2n(v[2])
+    out["err_class_distribution"] = e
+    v, e = try_call(lambda: hm.adjusted_homo(adj, labels))
+    out["out_adj_homo"], out["err_adj_homo"] = (t2n(v) if e == "" else np.nan), e
+    v, e = try_call(lambda: hm.label_informativeness(adj, labels))
+    out["out_label_info"], out["err_label_info"] = (t2n(v) if e == "" else np.nan), e
+
+
+def gram_metrics(adj_spmm, features, labels, out, sample_n, tag=""):
+    """similarity / gntk kernels / KR on `adj_spmm` (torch sparse, float32 values)."""
+    c = int(labels.max()) + 1
+    n = labels.shape[0]
+    oh = torch.eye(c)[labels]
+    out[f"out_soft_las{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=None, LP=1))
+    out[f"out_hard_las{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=1, LP=1))
+    out[f"out_soft_las_lp0{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=None, LP=0))
+    out[f"out_hard_las_lp0{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=1, LP=0))
+    out[f"out_soft_las_mean{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=None, LP=1, ifsum=0))
+    # idx_train branch (bool mask, as random_disassortative_splits returns)
+    seed_all(7)
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[torch.randperm(n)[: max(8, n // 3)]] = True
+    out[f"in_idx_train{tag}"] = t2n(mask)
+    out[f"out_soft_las_idx{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=None, LP=1, idx_train=mask))
+    out[f"out_hard_las_idx{tag}"] = t2n(hm.similarity(oh, adj_spmm, oh, hard=1, LP=1, idx_train=mask))
+    # GNTK / kernel-regression Gram matrices on a fixed sample
+    seed_all(11)
+    sample = np.sort(np.random.choice(n, size=min(sample_n, n), replace=False))
+    out[f"in_gntk_sample{tag}"] = sample
+    for nl in (0, 1):
+        kg, kx = hm.gntk_homophily_(features, adj_spmm, sample, nl)
+        out[f"out_gntk_KG_l{nl}{tag}"] = t2n(kg)
+        out[f"out_gntk_KX_l{nl}{tag}"] = t2n(kx)
+
+
+def kr_metric(adj_spmm, features, labels, out, sample_max, epochs, tag=""):
+    for clf in ("kernel_reg0", "kernel_reg1", "gnb"):
+        seed_all(2023)
+        p, _ = hm.classifier_based_performance_metric(features, adj_spmm, labels, sample_max,
+                                                      base_classifier=clf, epochs=epochs)
+        out[f"out_kr_p_{clf}{tag}"] = np.float64(p)
+    out[f"in_kr_sample_max{tag}"] = np.int64(sample_max)
+    out[f"in_kr_epochs{tag}"] = np.int64(epochs)
+    out[f"in_kr_seed{tag}"] = np.int64(2023)
+
+
+def spmm_projection(adj, features, out, tag):
+    """Store AX compactly: 24 seeded columns + row sums + a seeded 16-col random projection."""
+    ax = torch.spmm(adj, features)
+    g = torch.Generator().manual_seed(5)
+    d = features.shape[1]
+    cols = torch.randperm(d, generator=g)[: min(24, d)].sort().values
+    proj = torch.randn(d, 16, generator=g)
+    out[f"in_proj_cols_{tag}"] = t2n(cols)
+    out[f"in_proj_mat_seed_{tag}"] = np.int64(5)
+    out[f"out_ax_cols_{tag}"] = t2n(ax[:, cols])
+    out[f"out_ax_rowsum_{tag}"] = t2n(ax.double().sum(1))
+    out[f"out_ax_proj_{tag}"] = t2n(ax.double() @ proj.double())
+
+
+# --------------------------------------------------------------------------
+# case 1: Cora through the homophily_tests.py small-dataset flow
+# --------------------------------------------------------------------------
+def case_cora():
+    adj_sp, feats, labels = uf.load_data("cora")  # util_funcs.py:49
+    labels = torch.LongTensor(np.argmax(labels, axis=-1))
+    feats_sp = sp.csr_matrix(feats)
+    features_raw = torch.FloatTensor(np.asarray(feats.todense()))
+    A = uf.sparse_mx_to_torch_sparse_tensor(adj_sp).coalesce()  # raw, binary, no self-loops
+    n = labels.shape[0]
+    out = {}
+    out["in_n"] = np.int64(n)
+    out["in_edge_index"] = t2n(A.indices()).astype(np.int32)
+    out["in_labels"] = t2n(labels).astype(np.int64)
+    fcoo = feats_sp.tocoo()
+    out["in_feat_row"], out["in_feat_col"] = fcoo.row.astype(np.int32), fcoo.col.astype(np.int32)
+    out["in_feat_val"] = fcoo.data.astype(np.float32)
+    out["in_feat_dim"] = np.int64(features_raw.shape[1])
+
+    features = uf.normalize_tensor(features_raw)  # homophily_tests.py:80
+    out["out_features_rownorm_rowsum"] = t2n(features.double().sum(1))
+    for sym in (0, 1):
+        adjn = uf.normalize_tensor(torch.eye(n) + A.to_dense(), symmetric=sym).to_sparse().coalesce()  # :83-85
+        o = {}
+        structure_metrics(adjn, labels, o)
+        o["out_adj_values"] = t2n(adjn.values())
+        o["out_gen_edge_homo"] = t2n(hm.generalized_edge_homophily(adjn, features, labels))
+        spmm_projection(adjn, features, o, "norm")
+        for k, v in o.items():
+            out[f"{k}__sym{sym}"] = v
+    # aggregation homophily + KR are computed on the RAW adjacency (homophily_tests.py:120,135)
+    gram_metrics(A, features_raw, labels, out, sample_n=96)
+    kr_metric(A, features_raw, labels, out, sample_max=500, epochs=6)
+    # scipy-side normalisers of the LINKX flow (homophily_tests.py:99-104)
+    a_sym = uf.sparse_mx_to_torch_sparse_tensor(uf.sys_normalized_adjacency(adj_sp)).coalesce()
+    a_rw = uf.sparse_mx_to_torch_sparse_tensor(uf.row_normalized_adjacency(adj_sp)).coalesce()
+    out["out_sys_norm_values"] = t2n(a_sym.values())
+    out["out_row_norm_values"] = t2n(a_rw.values())
+    out["out_sys_norm_index"] = t2n(a_sym.indices()).astype(np.int32)
+    spmm_projection(a_sym, features, out, "sys")
+    spmm_projection(a_rw, features, out, "rw")
+    save("cora", **out)
+
+
+# --------------------------------------------------------------------------
+# case 2: data_synthesis graphs (ACM-GNN generator output shipped with the reference)
+# --------------------------------------------------------------------------
+def case_synthetic():
+    for nedge, h, s in ((800, 0.05, 0), (800, 0.5, 3), (4000, 0.2, 1), (4000, 0.9, 2)):
+        base = f"{REF}/data_synthesis/{nedge}/{h}"
+        adj = torch.load(f"{base}/adj_{h}_{s}.pt", weights_only=False).coalesce()
+        lab = torch.load(f"{base}/label_{h}_{s}.pt", weights_only=False).to_dense()
+        labels = torch.argmax(lab, 1)
+        n, c = lab.shape
+        # the shipped feature files are empty placeholders: draw class-conditional Gaussians instead
+        g = torch.Generator().manual_seed(100 + s)
+        centers = torch.randn(c, 32, generator=g)
+        features = (centers[labels] + 1.5 * torch.randn(n, 32, generator=g)).float()
+        A = coo_from_edges(t2n(adj.indices())[0], t2n(adj.indices())[1], n)  # float32 values
+        out = {"in_n": np.int64(n), "in_edge_index": t2n(A.indices()).astype(np.int32),
+               "in_labels": t2n(labels).astype(np.int64), "in_features": t2n(features)}
+        # sparse-side normalisation with self-loops, LINKX flow
+        a_sp = sp.coo_matrix((np.ones(A._nnz()), (t2n(A.indices())[0], t2n(A.indices())[1])), shape=(n, n))
+        for sym, fn in ((1, uf.sys_normalized_adjacency), (0, uf.row_normalized_adjacency)):
+            adjn = uf.sparse_mx_to_torch_sparse_tensor(fn(a_sp)).coalesce()
+            o = {}
+            structure_metrics(adjn, labels, o)
+            o["out_adj_values"] = t2n(adjn.values())
+            seed_all(3)  # the >=75000-entry branch draws edges with random.sample
+            o["out_gen_edge_homo"] = np.float64(hm.generalized_edge_homophily(adjn, features, labels))
+            o["in_gen_seed"] = np.int64(3)
+            spmm_projection(adjn, features, o, "norm")
+            gram_metrics(adjn, features, labels, o, sample_n=64, tag="_norm")
+            for k, v in o.items():
+                out[f"{k}__sym{sym}"] = v
+        gram_metrics(A, features, labels, out, sample_n=64)
+        kr_metric(A, features, labels, out, sample_max=300, epochs=4)
+        save(f"syn_{nedge}_{h}_{s}", **out)
+
+
+# --------------------------------------------------------------------------
+# case 3: small random graphs exercising the edge cases
+# --------------------------------------------------------------------------
+def case_edge_cases():
+    rng = np.random.default_rng(42)
+
+    def rand_graph(n, m, c, self_loops, neg_frac, undirected=True, isolated=0):
+        r = rng.integers(0, n - isolated, m)
+        q = rng.integers(0, n - isolated, m)
+        keep = r != q
+        r, q = r[keep], q[keep]
+        if undirected:
+            r, q = np.concatenate([r, q]), np.concatenate([q, r])
+        if self_loops == "all":
+            r, q = np.concatenate([r, np.arange(n)]), np.concatenate([q, np.arange(n)])
+        elif self_loops == "some":
+            k = np.arange(0, n, 3)
+            r, q = np.concatenate([r, k]), np.concatenate([q, k])
+        labels = rng.integers(0, c, n)
+        labels[rng.permutation(n)[:c]] = np.arange(c)  # every class present
+        if neg_frac > 0:
+            labels[rng.random(n) < neg_frac] = -1
+        return r, q, labels
+
+    specs = {
+        # name: (n, m, c, self_loops, neg_frac, undirected, isolated)
+        "ec_selfloops_all": (300, 900, 4, "all", 0.0, True, 0),
+        "ec_no_selfloops": (300, 900, 4, "none", 0.0, True, 0),
+        "ec_some_selfloops": (257, 700, 3, "some", 0.0, True, 0),
+        "ec_negative_labels": (400, 1500, 2, "all", 0.25, True, 0),
+        "ec_directed": (200, 800, 5, "all", 0.0, False, 0),
+        "ec_isolated_tail": (128, 300, 3, "none", 0.0, True, 9),
+        "ec_skewed": (500, 0, 6, "all", 0.0, True, 0),
+        "ec_many_classes": (600, 4000, 40, "all", 0.0, True, 0),
+    }
+    for name, (n, m, c, sl, neg, und, iso) in specs.items():
+        if name == "ec_skewed":  # star-heavy graph: a few hubs hold most edges
+            hubs = rng.integers(0, 5, 3000)
+            leaves = rng.integers(5, n, 3000)
+            r, q = np.concatenate([hubs, leaves, np.arange(n)]), np.concatenate([leaves, hubs, np.arange(n)])
+            labels = rng.integers(0, c, n)
+            labels[:c] = np.arange(c)
+        else:
+            r, q, labels = rand_graph(n, m, c, sl, neg, und, iso)
+        vals = rng.random(r.shape[0]).astype(np.float32) + 0.1
+        A = coo_from_edges(r, q, n, vals)  # coalesce() sums duplicate entries
+        labels_t = torch.from_numpy(labels.astype(np.int64))
+        features = torch.from_numpy(rng.standard_normal((n, 19)).astype(np.float32))
+        features[::17] = 0  # zero rows: cosine similarity NaN/0 handling
+        out = {"in_n": np.int64(n), "in_edge_index": t2n(A.indices()).astype(np.int32),
+               "in_edge_values": t2n(A.values()), "in_labels": labels.astype(np.int64),
+               "in_features": t2n(features)}
+        structure_metrics(A, labels_t, out, onehot=(neg == 0))
+        out["out_gen_edge_homo"] = t2n(hm.generalized_edge_homophily(A, features, labels_t))
+        seed_all(3)
+        v = hm.generalized_edge_homophily(A, features, labels_t, sample_max=200, iteration=3)
+        out["out_gen_edge_homo_sampled"] = np.float64(v)
+        out["in_gen_sampled_args"] = np.array([3, 200, 3], dtype=np.int64)  # seed, sample_max, iteration
+        spmm_projection(A, features, out, "w")
+        if neg == 0:
+            gram_metrics(A, features, labels_t, out, sample_n=48)
+        save(name, **out)
+
+
+if __name__ == "__main__":
+    case_cora()
+    case_synthetic()
+    case_edge_cases()
+    os.chdir(_cwd)
