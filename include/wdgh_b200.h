@@ -1,0 +1,205 @@
+/*
+ * wdgh_b200.h -- C ABI of the B200-native graph-statistics hot path.
+ *
+ * Drop-in boundary for the path BASELINE.json `north_star` names in
+ * SitaoLuan/When-Do-GNNs-Help:  A_hat X aggregation (SGC-1 / GCN propagation)
+ * plus the homophily / node-distinguishability metrics of
+ *     utils/homophily_metrics.py   and   utils/util_funcs.py.
+ * Each entry point cites the reference lines it replaces.  The reference is
+ * pure Python; its "FFI" for this path is a ctypes binding (see
+ * INTEGRATION.md), so every signature is plain pointers + sizes, no torch
+ * types.
+ *
+ * Conventions
+ *   - Pointers are DEVICE pointers on the current CUDA device unless the name
+ *     ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Calls are asynchronous on `stream` unless stated.
+ *   - A graph is CSR: rowptr int64[n+1], col int32[nnz] (row-major, the order
+ *     `A.coalesce().indices()` yields), optional val float32[nnz] (NULL = all 1).
+ *   - Labels are int32[n]; negative = unlabelled (LINKX convention, hm.py:48).
+ *   - Return value: 0 on success, a positive cudaError_t, or a negative
+ *     WDGH_E* code; wdgh_last_error() gives the message of the calling thread.
+ *   - There is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef WDGH_B200_H
+#define WDGH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WDGH_VERSION 100
+
+#define WDGH_EINVAL (-1)  /* bad argument                                   */
+#define WDGH_ENODEV (-2)  /* no sm_100 device / kernel image not loadable  */
+#define WDGH_ESTATE (-3)  /* plan / workspace too small or stale            */
+
+/* normalisation applied on the fly inside wdgh_spmm_csr */
+#define WDGH_NORM_NONE 0 /* Y = A X                       (torch.spmm(adj, x), hm.py:192,199,234)          */
+#define WDGH_NORM_RW   1 /* Y = D^-1 (A [+I]) X           (row_normalized_adjacency, util_funcs.py:383-390) */
+#define WDGH_NORM_SYM  2 /* Y = D^-1/2 (A [+I]) D^-1/2 X  (sys_normalized_adjacency, util_funcs.py:418-426) */
+
+/* ---- library ------------------------------------------------------------ */
+int         wdgh_version(void);
+const char *wdgh_last_error(void);
+/* sm count and compute capability of the current device */
+int         wdgh_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* kernels this library has launched since load (bench.py's "gpu_launches") */
+uint64_t    wdgh_launch_count(void);
+
+/* ---- formats (A.coalesce().indices() -> CSR; hm.py:50,63,127) ------------ */
+/* indices: torch COO layout int64[2][nnz], row-major sorted (coalesced).
+ * Writes rowptr int64[n+1] and col int32[nnz]. */
+int wdgh_coo_to_csr(const int64_t *indices, int64_t nnz, int64_t n,
+                    int64_t *rowptr, int32_t *col, void *stream);
+/* CSR -> explicit int64 row ids (the inverse; for handing indices back to torch) */
+int wdgh_csr_to_coo_rows(const int64_t *rowptr, int64_t n, int64_t nnz, int64_t *row, void *stream);
+/* int64 labels (torch.LongTensor) -> int32; *max_label (device int32) = max over n */
+int wdgh_pack_labels(const int64_t *labels, int64_t n, int32_t *out, int32_t *max_label, void *stream);
+/* argmax over the columns of a dense one-hot / score matrix -> int32 labels (hm.py:193) */
+int wdgh_argmax_rows(const float *m, int64_t n, int64_t c, int64_t ld, int32_t *out, void *stream);
+
+/* ---- load-balance plan (degree binning for skewed graphs) ---------------- */
+/* Rows with more than `heavy_threshold` entries are split into chunks of that
+ * many entries; everything else is handled one row per warp / sub-warp group.
+ * The plan lives in caller-provided device memory and is reused by
+ * wdgh_spmm_csr and wdgh_structure_counts for the same rowptr.
+ *   plan_i64  : int64[WDGH_PLAN_HEADER + 3*capacity]   (device)
+ *   capacity  : >= 2 * nnz / heavy_threshold + 2       (upper bound on the number of chunks)
+ *   plan_host : int64[4] HOST array the later calls take alongside plan_i64
+ * SYNCHRONOUS (reads the two counters back to size the later launches). */
+#define WDGH_PLAN_HEADER 8
+int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t heavy_threshold,
+                    int64_t *plan_i64, int64_t capacity,
+                    int64_t *plan_host /* int64[4] out: n_heavy, n_chunks, threshold, capacity */,
+                    void *stream);
+
+/* ---- normalisation (util_funcs.py:365-390, 418-426) ---------------------- */
+/* dinv[i] = (rowsum_i + self_loop)^p, p=-1 (RW) / -1/2 (SYM), inf -> 0, row sums
+ * of an all-zero row become 1 for SYM as in util_funcs.py:422.  val NULL = binary. */
+int wdgh_degree_scale(const int64_t *rowptr, const float *val, int64_t n,
+                      int norm, int add_self_loop, float *dinv /* nullable */,
+                      double *dinv64 /* nullable: the same scale before the float32 cast */, void *stream);
+/* Materialise the normalised values of a CSR that ALREADY contains its diagonal:
+ * out[e] = f32( dinv64_i * val[e] * dinv64_j ) (SYM) or f32( dinv64_i * val[e] ) (RW), i.e. the float64
+ * products scipy forms before sparse_mx_to_torch_sparse_tensor casts them (util_funcs.py:402). */
+int wdgh_scale_values(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                      int norm, const double *dinv64, float *out, void *stream);
+/* CSR of (A + I): merges / inserts the diagonal, keeping columns sorted.
+ * out_rowptr int64[n+1]; out_col / out_val sized nnz + n (upper bound);
+ * scratch int64[n + 2*ceil(n/1024) + 8].  The new nnz is out_rowptr[n]. */
+int wdgh_add_self_loops(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                        int64_t *out_rowptr, int32_t *out_col, float *out_val,
+                        int64_t *scratch, void *stream);
+/* Dense row normalisation, normalize_tensor(mx, symmetric) (util_funcs.py:365-380).
+ * symmetric != 0 needs a square matrix (n == d).  scratch_n: float32[n]. */
+int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
+                         int symmetric, float *scratch_n, float *out, int64_t ldo, void *stream);
+
+/* ---- A_hat X aggregation: CSR SpMM, float32 ------------------------------ */
+/* y[n][d] = norm(A [+ I]) x.   norm != NONE with val == NULL computes
+ * D^-1/2 / D^-1 from the row lengths on the fly -- A_hat is never materialised.
+ *   dinv     : float32[n] from wdgh_degree_scale (required iff norm != NONE)
+ *   plan_i64 / plan_host : from wdgh_plan_build (required)
+ *   partial  : float32[n_chunks * roundup(d,4)] scratch for split rows (may be NULL if n_chunks == 0)
+ * Replaces torch.spmm / torch.mm(adj, features) at hm.py:192,199,234,299,315. */
+int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                  const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
+                  int norm, int add_self_loop, const float *dinv,
+                  const int64_t *plan_i64, const int64_t *plan_host, float *partial, void *stream);
+
+/* ---- label metrics: one pass over the edges ------------------------------ */
+/* Integer statistics every label metric of homophily_metrics.py is a ratio of
+ * (edge / node / class / adjusted homophily, label informativeness; hm.py:43-161).
+ *   counters int64[WDGH_SC_HEADER + 2*C + C*C], zeroed by the call:
+ *     [WDGH_SC_MATCH_ALL]  stored entries with equal endpoint labels (self-loops included)   hm.py:51
+ *     [WDGH_SC_MATCH_LAB]  same, both endpoints labelled >= 0                               hm.py:52-54
+ *     [WDGH_SC_N_LAB]      stored entries with both endpoints labelled >= 0
+ *     [WDGH_SC_N_SELF]     stored diagonal entries
+ *     [WDGH_SC_N_EMPTY]    rows without any stored entry            (class_distribution IndexError)
+ *     [WDGH_SC_NBINS]      1 + max row id having an off-diagonal entry (node_homophily RuntimeError)
+ *     [WDGH_SC_N_NODES_NSL] rows with >= 1 off-diagonal entry                               hm.py:78
+ *     [WDGH_SC_HEADER + c]           nodes of class c                                        hm.py:114,137
+ *     [WDGH_SC_HEADER + C + c]       sum over class-c nodes of stored entries per row        hm.py:141
+ *     [WDGH_SC_HEADER + 2C + a*C+b]  off-diagonal entries a->b, both labelled                hm.py:97-100,144
+ *   node_sum double[1]: sum_i f32(match_i)/f32(deg_i) over rows with deg_i > 0 (off-diagonal)  hm.py:77-78
+ *   deg_nsl / match_nsl int32[n]: per-row off-diagonal entry count / label matches (scratch AND output)
+ */
+#define WDGH_SC_MATCH_ALL   0
+#define WDGH_SC_MATCH_LAB   1
+#define WDGH_SC_N_LAB       2
+#define WDGH_SC_N_SELF      3
+#define WDGH_SC_N_EMPTY     4
+#define WDGH_SC_NBINS       5
+#define WDGH_SC_N_NODES_NSL 6
+#define WDGH_SC_HEADER      8
+int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
+                          const int32_t *labels, int32_t num_classes,
+                          const int64_t *plan_i64, const int64_t *plan_host,
+                          int64_t *counters, double *node_sum,
+                          int32_t *deg_nsl, int32_t *match_nsl, void *stream);
+/* Same statistics from an arbitrary edge list (torch `edge_index` int64[2][E]: unsorted, repeats
+ * counted with multiplicity), as node_homophily_edge_idx / compact_matrix_edge_idx / our_measure
+ * receive it (hm.py:71,81,105).  Row lengths are unknown here, so the per-class degree mass
+ * [WDGH_SC_HEADER + C + c] and [WDGH_SC_N_EMPTY] stay 0. */
+int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,
+                              const int32_t *labels, int32_t num_classes,
+                              int64_t *counters, double *node_sum,
+                              int32_t *deg_nsl, int32_t *match_nsl, void *stream);
+/* edge_homophily with a 2-D label matrix (hm.py:50-56 as called from
+ * homophily_tests.py:115-116): counts elementwise-equal label entries over all
+ * stored (i,j); *equal_count (device uint64) out of nnz*c comparisons. */
+int wdgh_edge_label_rows_equal(const int64_t *rowptr, const int32_t *col, int64_t n,
+                               const float *label_rows, int64_t c, int64_t ld,
+                               unsigned long long *equal_count, void *stream);
+
+/* ---- generalised edge homophily: feature cosine over edges (hm.py:164-187) */
+/* mode 0: all off-diagonal stored entries whose value is > 0 (val NULL = all);
+ *         out_sum[0] += sum of cosines, out_cnt[0] += entries counted.
+ * mode 1: the `n_ids` stored-entry ids in `entry_ids` (position in the coalesced COO,
+ *         diagonal included); same outputs.  NaN cosines count as 0 (hm.py:168,185). */
+int wdgh_edge_cosine(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                     const float *x, int64_t d, int64_t ldx,
+                     int mode, const int64_t *entry_ids, int64_t n_ids,
+                     double *out_sum, unsigned long long *out_cnt, void *stream);
+
+/* ---- dense contractions: aggregation similarity and the KR Gram ---------- */
+/* g[m][m] = z z^T for z float32[m][d]  ((A X)(A X)^T, hm.py:192,199-200,234-235,246).
+ * Runs on tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM) when
+ * `use_tensor_cores` != 0, otherwise on a SIMT fp32 tile kernel. */
+int wdgh_gram(const float *z, int64_t m, int64_t d, int64_t ldz,
+              float *g, int64_t ldg, int use_tensor_cores, void *stream);
+/* gather rows: out[k][:] = x[ids[k]][:]  (torch indexing `[sample, :]`, hm.py:199,234,246) */
+int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const int64_t *ids, int64_t m,
+                     float *out, int64_t ldo, void *stream);
+/* w[m][C]: w[i][c] = sum (is_mean=0) or mean (is_mean=1) over j with labels[j]==c of g[i][j] (hm.py:201-206) */
+int wdgh_class_colsum(const float *g, int64_t m, int64_t ldg, const int32_t *labels, int32_t num_classes,
+                      int is_mean, float *w, void *stream);
+/* aggregation-similarity score from w (hm.py:207-229).  label_rows: float32[m][C] (the `label` argument).
+ * *count (device uint64) = number of nodes whose indicator is true; the score is count / m.
+ * scratch_c: float32[C]. */
+int wdgh_las_score(const float *w, const int32_t *labels, const float *label_rows, int64_t m, int32_t num_classes,
+                   int hard, int lp, int is_sum, float *scratch_c, unsigned long long *count, void *stream);
+/* in place: g <- arccos-kernel(g)/2 for n_layers==1, g/2 for n_layers==0 (hm.py:236-244,257).
+ * scratch_m: float32[m]. */
+int wdgh_gntk_transform(float *g, int64_t m, int64_t ldg, int n_layers, float *scratch_m, void *stream);
+
+/* ---- end-to-end entry with HOST buffers (bench.py "e2e") ------------------ */
+/* One pass of the hot path from host memory: H2D copy of the CSR, labels and
+ * features, plan + normaliser, Y = norm(A+I) X, the label statistics, D2H copy of
+ * the counters (+ node_sum) and, if y_host != NULL, of Y.  SYNCHRONOUS.
+ *   counters_host int64[WDGH_SC_HEADER + 2C + C*C], node_sum_host double[1].
+ * Device buffers are allocated once and cached inside the library between calls. */
+int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col_host, int64_t n, int64_t nnz,
+                       const float *x_host, int64_t d, const int32_t *labels_host, int32_t num_classes,
+                       int norm, int add_self_loop,
+                       float *y_host, int64_t *counters_host, double *node_sum_host);
+/* free the buffers cached by wdgh_pipeline_host */
+int wdgh_pipeline_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDGH_B200_H */

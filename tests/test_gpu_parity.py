@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI / the reference-named Python mirror) against
+(1) the golden outputs of the unmodified reference and (2) the CPU oracle on seeded inputs.
+
+Tolerances: integer statistics bit-exact; float results 1e-4 relative (BASELINE.json north_star),
+most are checked tighter.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+from oracle import ref_port as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def W():
+    import wdgh_b200
+    wdgh_b200._lib.require_device()
+    return wdgh_b200
+
+
+def close(a, b, rtol=RTOL, atol=1e-6):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol,
+                               atol=atol, equal_nan=True)
+
+
+def sparse(row, col, val, n):
+    idx = torch.from_numpy(np.vstack([row, col]).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(np.asarray(val, dtype=np.float32)), (n, n)).coalesce().cuda()
+
+
+def check_counts_exact(W, g, labels, row, col, n):
+    lab32, mx = W.graph.pack_labels(torch.from_numpy(labels))
+    s = W.graph.structure_counts(g, lab32, mx + 1)
+    o = O.structure_counts(row, col, labels, n)
+    assert s.match_all == o["match_all"] and s.match_lab == o["match_lab"] and s.n_lab == o["n_lab"]
+    assert s.n_self == o["n_selfloop"] and s.nnz == o["nnz"]
+    assert np.array_equal(s.hist, o["hist"])
+    assert np.array_equal(s.class_count, o["class_count"])
+    assert np.array_equal(s.deg_nsl.cpu().numpy().astype(np.int64), o["deg_nsl"])
+    assert np.array_equal(s.match_nsl.cpu().numpy().astype(np.int64), o["match_nsl"])
+    assert s.n_empty == int((o["deg_all"] == 0).sum())
+    assert s.n_nodes_nsl == int((o["deg_nsl"] > 0).sum())
+    lab = np.asarray(labels)
+    cd = np.array([o["deg_all"][lab == c].sum() for c in range(mx + 1)], dtype=np.int64)
+    assert np.array_equal(s.class_deg, cd)
+    return s
+
+
+def check_structure(W, z, A, row, col, labels, n, sfx=""):
+    hm = W.homophily_metrics
+    g = lambda k: z[k + sfx]  # noqa: E731
+    e = lambda k: str(z[k + sfx])  # noqa: E731
+    lab_t = torch.from_numpy(labels)
+    gr = hm._as_graph(A)
+    check_counts_exact(W, gr, labels, row, col, n)
+    close(hm.edge_homophily(A, lab_t), g("out_edge_homo"), rtol=1e-6)
+    if "out_edge_homo_onehot" + sfx in z.files:
+        c = int(labels.max()) + 1
+        close(hm.edge_homophily(A, torch.eye(c)[lab_t]), g("out_edge_homo_onehot"), rtol=1e-6)
+    close(hm.edge_homophily(A, labels, ignore_negative=True), g("out_edge_homo_ignore_negative"), rtol=1e-12)
+    with pytest.raises(TypeError):
+        hm.edge_homophily(A, lab_t, ignore_negative=True)
+    if e("err_node_homo"):
+        with pytest.raises(RuntimeError):
+            hm.node_homophily(A, lab_t)
+    else:
+        close(hm.node_homophily(A, lab_t), g("out_node_homo"), rtol=1e-6)
+    ei = torch.from_numpy(np.vstack([row, col]).astype(np.int64))
+    close(hm.compact_matrix_edge_idx(ei, lab_t), g("out_compat"), rtol=1e-6)
+    close(hm.our_measure(ei, lab_t), g("out_class_homo"), rtol=1e-5)
+    # shuffled edge list: same answer (edge-list kernel, atomics path)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    close(hm.our_measure(ei[:, perm], lab_t), g("out_class_homo"), rtol=1e-5)
+    if not e("err_node_homo"):
+        close(hm.node_homophily_edge_idx(ei[:, perm], lab_t, n), g("out_node_homo"), rtol=1e-6)
+    if e("err_class_distribution"):
+        for fn in (hm.class_distribution, hm.adjusted_homo, hm.label_informativeness):
+            with pytest.raises(IndexError):
+                fn(A, lab_t)
+    else:
+        p, p_bar, pc = hm.class_distribution(A, lab_t)
+        close(p, g("out_p"), rtol=1e-6)
+        close(p_bar, g("out_p_bar"), rtol=1e-6)
+        close(pc, g("out_pc"), rtol=1e-6)
+        close(hm.adjusted_homo(A, lab_t), g("out_adj_homo"), rtol=RTOL)
+        close(hm.label_informativeness(A, lab_t), g("out_label_info"), rtol=RTOL, atol=1e-5)
+
+
+def check_ax(z, ax, d, tag, rtol=RTOL):
+    ax = ax.detach().cpu().numpy()
+    cols, proj = G.proj_matrix(d)
+    scale = max(1e-6, float(np.abs(z[f"out_ax_cols_{tag}"]).max()))
+    close(ax[:, cols], z[f"out_ax_cols_{tag}"], rtol=rtol, atol=1e-6 * scale)
+    close(ax.astype(np.float64).sum(1), z[f"out_ax_rowsum_{tag}"], rtol=rtol, atol=1e-5 * scale)
+    close(ax.astype(np.float64) @ proj, z[f"out_ax_proj_{tag}"], rtol=rtol, atol=1e-4 * scale)
+
+
+def check_gram(W, z, A, x, labels, tag=""):
+    hm = W.homophily_metrics
+    c = int(labels.max()) + 1
+    oh = torch.eye(c)[torch.from_numpy(labels)]
+    n = labels.shape[0]
+    tol = 1.5 / n  # at most one node whose indicator sits on a float tie may flip (documented in DESIGN.md)
+    close(hm.similarity(oh, A, oh, hard=None, LP=1), z[f"out_soft_las{tag}"], rtol=0, atol=tol)
+    close(hm.similarity(oh, A, oh, hard=1, LP=1), z[f"out_hard_las{tag}"], rtol=0, atol=tol)
+    close(hm.similarity(oh, A, oh, hard=None, LP=0), z[f"out_soft_las_lp0{tag}"], rtol=0, atol=tol)
+    close(hm.similarity(oh, A, oh, hard=1, LP=0), z[f"out_hard_las_lp0{tag}"], rtol=0, atol=tol)
+    close(hm.similarity(oh, A, oh, hard=None, LP=1, ifsum=0), z[f"out_soft_las_mean{tag}"], rtol=0, atol=tol)
+    m = torch.from_numpy(z[f"in_idx_train{tag}"])
+    tol_m = 1.5 / int(m.sum())
+    close(hm.similarity(oh, A, oh, hard=None, LP=1, idx_train=m), z[f"out_soft_las_idx{tag}"], rtol=0, atol=tol_m)
+    close(hm.similarity(oh, A, oh, hard=1, LP=1, idx_train=m), z[f"out_hard_las_idx{tag}"], rtol=0, atol=tol_m)
+    sample = z[f"in_gntk_sample{tag}"]
+    xt = torch.from_numpy(x)
+    for nl in (0, 1):
+        kg, kx = hm.gntk_homophily_(xt, A, sample, nl)
+        for got, key in ((kg, f"out_gntk_KG_l{nl}{tag}"), (kx, f"out_gntk_KX_l{nl}{tag}")):
+            scale = max(1.0, float(np.abs(z[key]).max()))
+            close(got, z[key], rtol=RTOL, atol=2e-5 * scale)
+
+
+def check_kr(W, z, A, x, labels, tag=""):
+    hm = W.homophily_metrics
+    for clf in ("kernel_reg0", "kernel_reg1", "gnb"):
+        seed = int(z[f"in_kr_seed{tag}"])
+        random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
+        p, _ = hm.classifier_based_performance_metric(torch.from_numpy(x), A, torch.from_numpy(labels),
+                                                      int(z[f"in_kr_sample_max{tag}"]), base_classifier=clf,
+                                                      epochs=int(z[f"in_kr_epochs{tag}"]))
+        # the p-value is a function of per-epoch accuracies (multiples of 1/n_val): equal unless an argmax flips
+        close(p, z[f"out_kr_p_{clf}{tag}"], rtol=5e-2, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+def test_cora(W):
+    uf, hm = W.util_funcs, W.homophily_metrics
+    z = G.load("cora")
+    n = int(z["in_n"])
+    labels = z["in_labels"]
+    ei = z["in_edge_index"].astype(np.int64)
+    x_raw = G.cora_dense_features(z)
+    x = uf.normalize_tensor(torch.from_numpy(x_raw))          # homophily_tests.py:80
+    close(x.double().sum(1), z["out_features_rownorm_rowsum"], rtol=1e-5)
+    ones = np.ones(ei.shape[1], np.float32)
+    A_raw = sparse(ei[0], ei[1], ones, n)
+    for sym in (0, 1):
+        row, col, val = G.dense_normalized_with_self_loops(z, sym)
+        A = sparse(row, col, val, n)
+        check_structure(W, z, A, row, col, labels, n, f"__sym{sym}")
+        close(hm.generalized_edge_homophily(A, x, torch.from_numpy(labels)), z[f"out_gen_edge_homo__sym{sym}"])
+        check_ax(z, W.spmm(hm._as_graph(A), x), x.shape[1], f"norm__sym{sym}")
+        # the same A_hat X without materialising A_hat: on-the-fly normalisation of the raw graph
+        g_raw = W.CSRGraph.from_torch_sparse(A_raw, binary=True)
+        y = W.spmm(g_raw, x, W.NORM_SYM if sym else W.NORM_RW, True)
+        check_ax(z, y, x.shape[1], f"norm__sym{sym}")
+    check_gram(W, z, A_raw, x_raw, labels)
+    check_kr(W, z, A_raw, x_raw, labels)
+    # LINKX flow normalisers (homophily_tests.py:99-104)
+    for name, fn, tag in (("out_sys_norm_values", uf.sys_normalized_adjacency, "sys"),
+                          ("out_row_norm_values", uf.row_normalized_adjacency, "rw")):
+        gn = fn(A_raw)
+        t = uf.sparse_mx_to_torch_sparse_tensor(gn)
+        assert np.array_equal(t.indices().cpu().numpy(), z["out_sys_norm_index"])
+        close(t.values(), z[name], rtol=1e-6)
+        check_ax(z, W.spmm(gn, x), x.shape[1], tag)
+        check_ax(z, uf.propagate(A_raw, x, symmetric=(tag == "sys")), x.shape[1], tag)
+
+
+@pytest.mark.parametrize("name", G.names("syn_"))
+def test_synthetic(W, name):
+    uf, hm = W.util_funcs, W.homophily_metrics
+    z = G.load(name)
+    n = int(z["in_n"])
+    labels = z["in_labels"]
+    ei = z["in_edge_index"].astype(np.int64)
+    x = z["in_features"]
+    xt = torch.from_numpy(x)
+    ones = np.ones(ei.shape[1], np.float32)
+    A_raw = sparse(ei[0], ei[1], ones, n)
+    for sym, fn, ofn in ((1, uf.sys_normalized_adjacency, O.sys_normalized_adjacency),
+                         (0, uf.row_normalized_adjacency, O.row_normalized_adjacency)):
+        sfx = f"__sym{sym}"
+        A = uf.sparse_mx_to_torch_sparse_tensor(fn(A_raw))
+        close(A.values(), z["out_adj_values" + sfx], rtol=1e-6)
+        row, col, _ = ofn(ei[0], ei[1], ones, n)
+        check_structure(W, z, A, row, col, labels, n, sfx)
+        seed = int(z["in_gen_seed" + sfx])
+        random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
+        close(hm.generalized_edge_homophily(A, xt, torch.from_numpy(labels)), z["out_gen_edge_homo" + sfx])
+        check_ax(z, W.spmm(hm._as_graph(A), xt), x.shape[1], "norm" + sfx)
+        check_ax(z, uf.propagate(A_raw, xt, symmetric=sym), x.shape[1], "norm" + sfx)
+        zz = {k.replace("_norm" + sfx, "") + "@": z[k] for k in z.files if k.endswith("_norm" + sfx)}
+
+        class _Z(dict):
+            files = list(zz)
+        check_gram(W, _Z(zz), A, x, labels, tag="@")
+    check_gram(W, z, A_raw, x, labels)
+    check_kr(W, z, A_raw, x, labels)
+
+
+@pytest.mark.parametrize("name", G.names("ec_"))
+def test_edge_cases(W, name):
+    hm = W.homophily_metrics
+    z = G.load(name)
+    n = int(z["in_n"])
+    labels = z["in_labels"]
+    ei = z["in_edge_index"].astype(np.int64)
+    val = z["in_edge_values"]
+    x = z["in_features"]
+    xt = torch.from_numpy(x)
+    A = sparse(ei[0], ei[1], val, n)
+    check_structure(W, z, A, ei[0], ei[1], labels, n)
+    close(hm.generalized_edge_homophily(A, xt, None), z["out_gen_edge_homo"], atol=1e-6)
+    seed, smax, it = (int(v) for v in z["in_gen_sampled_args"])
+    random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
+    close(hm.generalized_edge_homophily(A, xt, None, sample_max=smax, iteration=it), z["out_gen_edge_homo_sampled"],
+          atol=1e-6)
+    check_ax(z, W.spmm(hm._as_graph(A), xt), x.shape[1], "w")
+    if "out_soft_las" in z.files:
+        check_gram(W, z, A, x, labels)
+
+
+# ---------------------------------------------------------------------------
+# seeded random graphs against the oracle: skew (split rows), every feature-width code path
+# ---------------------------------------------------------------------------
+def powerlaw_graph(n, avg_deg, seed, hubs=3, hub_deg=3000, self_loops=False):
+    rng = np.random.default_rng(seed)
+    deg = np.minimum((rng.pareto(1.8, n) + 1) * avg_deg / 2.2, n // 2).astype(np.int64)
+    src = np.repeat(np.arange(n), deg)
+    dst = rng.integers(0, n, src.shape[0])
+    hs = np.repeat(np.arange(hubs), hub_deg)
+    hd = rng.integers(0, n, hs.shape[0])
+    src, dst = np.concatenate([src, hs, hd]), np.concatenate([dst, hd, hs])
+    if self_loops:
+        src, dst = np.concatenate([src, np.arange(n)]), np.concatenate([dst, np.arange(n)])
+    return O.coalesce(src, dst, None, n)
+
+
+@pytest.mark.parametrize("d", [1, 3, 4, 8, 19, 32, 64, 100, 128, 130, 256, 384, 512, 700])
+def test_spmm_widths_vs_oracle(W, d):
+    n = 3000
+    row, col, val = powerlaw_graph(n, 6, seed=d)
+    rng = np.random.default_rng(d)
+    val = (rng.random(row.shape[0]) + 0.5).astype(np.float32)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), torch.from_numpy(val), n, threshold=256)
+    assert g.n_heavy >= 3 and g.n_chunks > g.n_heavy
+    y = W.spmm(g, torch.from_numpy(x)).cpu().numpy()
+    ref = O.spmm(row, col, val, n, x)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("norm,self_loop", [(1, True), (2, True), (1, False), (2, False)])
+def test_spmm_on_the_fly_norm_vs_oracle(W, norm, self_loop):
+    n, d = 5000, 128
+    row, col, _ = powerlaw_graph(n, 10, seed=7)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    ones = np.ones(row.shape[0], np.float32)
+    x = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), None, n)
+    y = W.spmm(g, torch.from_numpy(x), norm, self_loop).cpu().numpy()
+    if self_loop:
+        fn = O.sys_normalized_adjacency if norm == 2 else O.row_normalized_adjacency
+        r, c, v = fn(row, col, ones, n)
+    else:  # same normalisers without the +I: scale the raw matrix
+        deg = np.bincount(row, minlength=n).astype(np.float64)
+        if norm == 2:
+            dis = np.where(deg > 0, 1 / np.sqrt(np.where(deg > 0, deg, 1)), 1.0)
+            v = (dis[row] * dis[col]).astype(np.float32)
+        else:
+            v = (1 / deg[row]).astype(np.float32)
+        r, c = row, col
+    ref = O.spmm(r, c, v, n, x)
+    np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("c,avg", [(2, 3), (7, 9), (10, 20), (40, 40), (70, 5)])
+def test_structure_counts_vs_oracle(W, c, avg):
+    n = 20000
+    row, col, _ = powerlaw_graph(n, avg, seed=c, self_loops=(c % 2 == 0))
+    rng = np.random.default_rng(c)
+    labels = rng.integers(0, c, n).astype(np.int64)
+    labels[:c] = np.arange(c)
+    if c == 2:
+        labels[rng.random(n) < 0.2] = -1
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), None, n, threshold=128)
+    assert g.n_heavy > 0
+    s = check_counts_exact(W, g, labels, row, col, n)
+    assert s.hist.sum() == s.n_lab - int(((row == col) & (labels[row] >= 0)).sum())
+
+
+def test_properties_large(W):
+    """Size-independent properties at a size the oracle is not run on (2M nodes, ~40M entries)."""
+    n, d = 2_000_000, 128
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    deg = torch.randint(0, 40, (n,), device="cuda", generator=gen)
+    deg[:4] = 300_000  # hubs -> split rows
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    rowptr[1:] = torch.cumsum(deg, 0)
+    nnz = int(rowptr[-1])
+    col = torch.randint(0, n, (nnz,), device="cuda", generator=gen, dtype=torch.int32)
+    g = W.CSRGraph.from_csr(rowptr, col, None, n)
+    assert g.n_heavy == 4
+    x1 = torch.randn(n, d, device="cuda", generator=gen)
+    x2 = torch.randn(n, d, device="cuda", generator=gen)
+    # linearity
+    y1, y2 = W.spmm(g, x1, W.NORM_SYM, True), W.spmm(g, x2, W.NORM_SYM, True)
+    y12 = W.spmm(g, x1 + 2 * x2, W.NORM_SYM, True)
+    err = (y12 - (y1 + 2 * y2)).abs().max().item()
+    assert err <= 1e-4 * y12.abs().max().item()
+    # row-stochastic: D^-1 (A+I) 1 = 1
+    ones = torch.ones(n, 4, device="cuda")
+    yo = W.spmm(g, ones, W.NORM_RW, True)
+    assert (yo - 1).abs().max().item() < 1e-5
+    # unnormalised A 1 = row lengths, exactly
+    yd = W.spmm(g, ones, W.NORM_NONE, False)
+    assert torch.equal(yd[:, 0].to(torch.int64), deg.to(torch.int64))
+    # deterministic
+    assert torch.equal(y1, W.spmm(g, x1, W.NORM_SYM, True))
+    # label statistics: histogram total, per-node degrees, symmetry under label permutation
+    c = 10
+    labels = torch.randint(0, c, (n,), device="cuda", generator=gen)
+    lab32, mx = W.graph.pack_labels(labels)
+    s = W.graph.structure_counts(g, lab32, c)
+    assert s.hist.sum() + s.n_self == nnz == s.n_lab
+    assert s.match_all == int(np.trace(s.hist)) + s.n_self
+    assert int(s.deg_nsl.sum()) == nnz - s.n_self
+    cd = torch.zeros(c, dtype=torch.int64, device="cuda").scatter_add_(0, labels, deg.to(torch.int64))
+    assert np.array_equal(s.class_deg, cd.cpu().numpy())
+    perm = torch.randperm(c, device="cuda", generator=gen)
+    s2 = W.graph.structure_counts(g, perm[labels].to(torch.int32), c)
+    p = perm.cpu().numpy()
+    assert np.array_equal(s2.hist[np.ix_(p, p)], s.hist)
+    assert s2.match_all == s.match_all and abs(s2.node_sum - s.node_sum) < 1e-6 * max(1.0, s.node_sum)
+
+
+def test_gram_vs_torch_fp64(W):
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for m, d in ((1, 1), (63, 7), (64, 16), (500, 1433), (1000, 10), (777, 130)):
+        z = torch.randn(m, d, device="cuda", generator=gen)
+        ref = (z.double() @ z.double().T)
+        got = W.graph.gram(z, use_tensor_cores=False)
+        assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_abi_rejects_bad_arguments(W):
+    import ctypes as C
+    lib = W._lib.lib
+    assert lib.wdgh_spmm_csr(None, None, None, 4, None, 4, 4, None, 4, 0, 0, None, None, None, None, None) == -1
+    assert b"null pointer" in lib.wdgh_last_error()
+    host = (C.c_int64 * 4)()
+    assert lib.wdgh_plan_build(None, 4, 512, None, 4, host, None) == -1
+    with pytest.raises(ValueError):
+        g = W.CSRGraph.from_csr(torch.zeros(5, dtype=torch.int64), torch.zeros(0, dtype=torch.int32), None, 4)
+        W.spmm(g, torch.zeros(3, 2))
+
+
+def test_empty_graph(W):
+    g = W.CSRGraph.from_coo_indices(torch.zeros(2, 0, dtype=torch.int64), None, 5)
+    assert g.rowptr.cpu().tolist() == [0] * 6
+    y = W.spmm(g, torch.ones(5, 8))
+    assert not y.any()
+    lab32, mx = W.graph.pack_labels(torch.tensor([0, 1, 0, 1, 1]))
+    s = W.graph.structure_counts(g, lab32, 2)
+    assert s.match_all == 0 and s.hist.sum() == 0 and s.n_empty == 5
+    assert torch.isnan(W.homophily_metrics.edge_homophily(g, torch.tensor([0, 1, 0, 1, 1])))

@@ -1,0 +1,378 @@
+// Label metrics: every integer statistic behind edge / node / class / adjusted homophily and
+// label informativeness (utils/homophily_metrics.py:43-161) in ONE pass over the stored entries.
+//
+//   edge pass  : per entry (i,j): label gather, match flags, class-pair key a*C+b.
+//                Key multiplicities inside a warp are folded with __match_any_sync + popc and a
+//                single shared-memory atomic per distinct key (C*C <= 4096 bins in shared memory,
+//                global 64-bit atomics beyond that); the scalar counters travel as per-lane
+//                registers and are combined by warp shuffles -- all counts are exact integers.
+//   node pass  : per node: f32(match)/f32(deg) for node homophily (hm.py:77-78), class sizes,
+//                class degree mass (hm.py:141), empty rows, bincount length.
+// HBM traffic per entry: 4 B of `col` plus one label gather that is served by L2 whenever the
+// label array (4 B/node) fits its 126 MB.
+#include "common.cuh"
+
+namespace wdgh {
+
+constexpr int kHistSmemBins = 4096;
+
+struct EdgeAcc {
+  unsigned match_all = 0, match_lab = 0, n_lab = 0, n_self = 0;
+};
+
+// Folds one warp-wide batch of class-pair keys (key < 0: nothing to count) into the histogram.
+__device__ __forceinline__ void fold_keys(int key, unsigned *s_hist, unsigned long long *g_hist, bool use_smem) {
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
+    const unsigned c = __popc(peers);
+    if (use_smem) atomicAdd(&s_hist[key], c);
+    else atomicAdd(&g_hist[key], (unsigned long long)c);
+  }
+}
+
+__device__ __forceinline__ void visit(int64_t row, int li, int j, int lj, int C, EdgeAcc &a, int &m_nsl, int &d_nsl,
+                                      int &key) {
+  const bool self = (j == row);
+  const bool same = (li == lj);
+  const bool both = (li >= 0) && (lj >= 0);
+  a.match_all += same;
+  a.match_lab += (same && both);
+  a.n_lab += both;
+  a.n_self += self;
+  if (!self) {
+    d_nsl += 1;
+    m_nsl += same;
+    if (both) key = li * C + lj;
+  }
+}
+
+__device__ __forceinline__ void flush(EdgeAcc &a, unsigned long long *counters) {
+  long long v0 = warp_sum((long long)a.match_all), v1 = warp_sum((long long)a.match_lab);
+  long long v2 = warp_sum((long long)a.n_lab), v3 = warp_sum((long long)a.n_self);
+  if ((threadIdx.x & 31) == 0) {
+    if (v0) atomicAdd(&counters[WDGH_SC_MATCH_ALL], (unsigned long long)v0);
+    if (v1) atomicAdd(&counters[WDGH_SC_MATCH_LAB], (unsigned long long)v1);
+    if (v2) atomicAdd(&counters[WDGH_SC_N_LAB], (unsigned long long)v2);
+    if (v3) atomicAdd(&counters[WDGH_SC_N_SELF], (unsigned long long)v3);
+  }
+}
+
+// G lanes per row, persistent grid.  Split (heavy) rows get deg/match = 0 here and are
+// completed by structure_chunks_kernel.
+template <int G>
+__global__ void __launch_bounds__(256)
+structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
+                      const int32_t *__restrict__ labels, int C, int64_t threshold,
+                      unsigned long long *__restrict__ counters, int32_t *__restrict__ deg_nsl,
+                      int32_t *__restrict__ match_nsl) {
+  extern __shared__ unsigned s_hist[];
+  const bool use_smem = (C * C <= kHistSmemBins);
+  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+  }
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, grp = lane / G;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  EdgeAcc acc;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * RPW < n; w += nwarps) {
+    const int64_t row = w * RPW + grp;
+    int64_t s = 0, e = 0;
+    int li = -1;
+    bool mine = false;
+    if (row < n) {
+      s = __ldg(rowptr + row);
+      e = __ldg(rowptr + row + 1);
+      mine = (e - s) <= threshold;
+      if (!mine) e = s;
+      li = __ldg(labels + row);
+    }
+    const int iters = warp_max((int)((e - s + G - 1) / G));
+    int m_nsl = 0, d_nsl = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int64_t idx = s + (int64_t)it * G + gl;
+      int key = -1;
+      if (idx < e) {
+        const int j = __ldg(col + idx);
+        const int lj = __ldg(labels + j);
+        visit(row, li, j, lj, C, acc, m_nsl, d_nsl, key);
+      }
+      fold_keys(key, s_hist, g_hist, use_smem);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      m_nsl += __shfl_xor_sync(0xffffffffu, m_nsl, o);
+      d_nsl += __shfl_xor_sync(0xffffffffu, d_nsl, o);
+    }
+    if (gl == 0 && row < n) {  // heavy rows: zero, the chunk kernel adds atomically
+      deg_nsl[row] = d_nsl;
+      match_nsl[row] = m_nsl;
+    }
+  }
+  flush(acc, counters);
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) {
+      const unsigned v = s_hist[b];
+      if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
+    }
+  }
+}
+
+// One warp per chunk of a split row.
+__global__ void __launch_bounds__(256)
+structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                        const int32_t *__restrict__ labels, int C, const int64_t *__restrict__ plan,
+                        int64_t n_chunks, unsigned long long *__restrict__ counters,
+                        int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl) {
+  extern __shared__ unsigned s_hist[];
+  const bool use_smem = (C * C <= kHistSmemBins);
+  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t cap = plan[kPlanCapacity], T = plan[kPlanThreshold];
+  EdgeAcc acc;
+  for (int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += nwarps) {
+    const int64_t k = plan_chunk_owner(plan, cap)[chunk];
+    const int64_t row = plan_heavy_row(plan)[k];
+    const int64_t part = chunk - plan_heavy_chunk0(plan, cap)[k];
+    const int64_t s = __ldg(rowptr + row) + part * T;
+    const int64_t e = min(s + T, __ldg(rowptr + row + 1));
+    const int li = __ldg(labels + row);
+    int m_nsl = 0, d_nsl = 0;
+    for (int64_t base = s; base < e; base += 32) {  // warp-uniform trip count
+      const int64_t idx = base + lane;
+      int key = -1;
+      if (idx < e) {
+        const int j = __ldg(col + idx);
+        const int lj = __ldg(labels + j);
+        visit(row, li, j, lj, C, acc, m_nsl, d_nsl, key);
+      }
+      fold_keys(key, s_hist, g_hist, use_smem);
+    }
+    m_nsl = (int)warp_sum((long long)m_nsl);
+    d_nsl = (int)warp_sum((long long)d_nsl);
+    if (lane == 0) {
+      atomicAdd(&deg_nsl[row], d_nsl);
+      atomicAdd(&match_nsl[row], m_nsl);
+    }
+  }
+  flush(acc, counters);
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) {
+      const unsigned v = s_hist[b];
+      if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
+    }
+  }
+}
+
+// Edge-list input (an arbitrary, possibly unsorted / repeated `edge_index` as handed to
+// node_homophily_edge_idx / compact_matrix_edge_idx, hm.py:71,81): one lane per listed edge,
+// per-node counts through 32-bit global atomics.  deg / match must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+structure_coo_kernel(const int64_t *__restrict__ edge_index, int64_t E, int64_t n,
+                     const int32_t *__restrict__ labels, int C, unsigned long long *__restrict__ counters,
+                     int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl) {
+  extern __shared__ unsigned s_hist[];
+  const bool use_smem = (C * C <= kHistSmemBins);
+  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+  }
+  EdgeAcc acc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (E + stride - 1) / stride;  // uniform trip count for the warp-wide fold
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t t = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int key = -1;
+    if (t < E) {
+      const int64_t src = edge_index[t], dst = edge_index[E + t];
+      const int li = __ldg(labels + src), lj = __ldg(labels + dst);
+      int m = 0, d = 0;
+      visit(src, li, (int)dst, lj, C, acc, m, d, key);
+      if (d) atomicAdd(&deg_nsl[src], 1);
+      if (m) atomicAdd(&match_nsl[src], 1);
+    }
+    fold_keys(key, s_hist, g_hist, use_smem);
+  }
+  flush(acc, counters);
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < C * C; b += blockDim.x) {
+      const unsigned v = s_hist[b];
+      if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
+    }
+  }
+}
+
+// Per-node reductions.  Shared memory: 2*C 64-bit class accumulators when C <= 2048.
+__global__ void __launch_bounds__(256)
+structure_nodes_kernel(const int64_t *__restrict__ rowptr, int64_t n, const int32_t *__restrict__ labels, int C,
+                       const int32_t *__restrict__ deg_nsl, const int32_t *__restrict__ match_nsl,
+                       unsigned long long *__restrict__ counters, double *__restrict__ node_sum) {
+  extern __shared__ unsigned long long s_cls[];  // [C] class_count, [C] class_deg
+  const bool use_smem = (C <= 2048);
+  unsigned long long *g_cls = counters + WDGH_SC_HEADER;
+  if (use_smem) {
+    for (int b = threadIdx.x; b < 2 * C; b += blockDim.x) s_cls[b] = 0ull;
+    __syncthreads();
+  }
+  unsigned long long *cls = use_smem ? s_cls : g_cls;
+  double sum = 0.0;
+  long long n_nsl = 0, n_empty = 0, nbins = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int d = deg_nsl[i], m = match_nsl[i];
+    const int64_t deg_all = rowptr ? rowptr[i + 1] - rowptr[i] : 1;  // edge-list input: row lengths unknown
+    if (d > 0) {
+      sum += (double)((float)m / (float)d);  // float32 division as torch does (hm.py:77)
+      n_nsl += 1;
+      nbins = i + 1;  // i is increasing per thread
+    }
+    if (deg_all == 0) n_empty += 1;
+    const int l = labels[i];
+    if (l >= 0 && l < C) {
+      atomicAdd(&cls[l], 1ull);
+      if (rowptr) atomicAdd(&cls[C + l], (unsigned long long)deg_all);
+    }
+  }
+  sum = warp_sum(sum);
+  n_nsl = warp_sum(n_nsl);
+  n_empty = warp_sum(n_empty);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nbins = max(nbins, __shfl_xor_sync(0xffffffffu, nbins, o));
+  if ((threadIdx.x & 31) == 0) {
+    if (sum != 0.0) atomicAdd(node_sum, sum);
+    if (n_nsl) atomicAdd(&counters[WDGH_SC_N_NODES_NSL], (unsigned long long)n_nsl);
+    if (n_empty) atomicAdd(&counters[WDGH_SC_N_EMPTY], (unsigned long long)n_empty);
+    if (nbins) atomicMax(&counters[WDGH_SC_NBINS], (unsigned long long)nbins);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2 * C; b += blockDim.x) {
+      const unsigned long long v = s_cls[b];
+      if (v) atomicAdd(&g_cls[b], v);
+    }
+  }
+}
+
+// edge_homophily with a 2-D label matrix: elementwise equality of the two label rows (hm.py:51)
+__global__ void __launch_bounds__(256)
+label_rows_equal_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
+                        const float *__restrict__ lab, int64_t c, int64_t ld, unsigned long long *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  long long cnt = 0;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    const float *li = lab + row * ld;
+    for (int64_t q = s + lane; q < e; q += 32) {
+      const float *lj = lab + (int64_t)col[q] * ld;
+      for (int64_t k = 0; k < c; ++k) cnt += (li[k] == lj[k]);
+    }
+  }
+  cnt = warp_sum(cnt);
+  if (lane == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
+template <int G>
+static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels, int C,
+                       int64_t threshold, unsigned long long *counters, int32_t *deg, int32_t *match,
+                       size_t smem, cudaStream_t st) {
+  const int64_t ctas = ceil_div(n, (int64_t)8 * (32 / G));
+  structure_rows_kernel<G><<<persistent_grid(ctas, 8), 256, smem, st>>>(rowptr, col, n, labels, C, threshold, counters,
+                                                                       deg, match);
+  WDGH_LAUNCHED("structure_rows_kernel");
+  return 0;
+}
+
+}  // namespace wdgh
+
+using namespace wdgh;
+
+extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
+                                     const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
+                                     const int64_t *plan_host, int64_t *counters, double *node_sum,
+                                     int32_t *deg_nsl, int32_t *match_nsl, void *stream) {
+  WDGH_REQUIRE(rowptr && labels && plan_i64 && plan_host && counters && node_sum && deg_nsl && match_nsl,
+               "wdgh_structure_counts: null pointer");
+  WDGH_REQUIRE(n >= 0 && nnz >= 0 && (col || nnz == 0), "wdgh_structure_counts: bad shape");
+  WDGH_REQUIRE(num_classes >= 1 && num_classes <= 46340, "wdgh_structure_counts: num_classes out of range");
+  cudaStream_t st = as_stream(stream);
+  const int C = num_classes;
+  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
+  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
+  if (n == 0) return 0;
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
+  const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
+  const int64_t threshold = plan_host[2], n_chunks = plan_host[1];
+  const double avg = (double)nnz / (double)n;
+  int rc;
+  if (avg <= 6.0) rc = launch_rows<4>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
+  else if (avg <= 12.0) rc = launch_rows<8>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
+  else if (avg <= 24.0) rc = launch_rows<16>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
+  else rc = launch_rows<32>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
+  if (rc) return rc;
+  if (n_chunks > 0) {
+    structure_chunks_kernel<<<persistent_grid(ceil_div(n_chunks, 8), 8), 256, hist_smem, st>>>(
+        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl);
+    WDGH_LAUNCHED("structure_chunks_kernel");
+  }
+  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
+  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
+                                                                                     match_nsl, cnt, node_sum);
+  WDGH_LAUNCHED("structure_nodes_kernel");
+  return 0;
+}
+
+extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,
+                                         const int32_t *labels, int32_t num_classes, int64_t *counters,
+                                         double *node_sum, int32_t *deg_nsl, int32_t *match_nsl, void *stream) {
+  WDGH_REQUIRE(labels && counters && node_sum && deg_nsl && match_nsl && (edge_index || num_edges == 0),
+               "wdgh_structure_counts_coo: null pointer");
+  WDGH_REQUIRE(n >= 0 && num_edges >= 0 && num_classes >= 1 && num_classes <= 46340,
+               "wdgh_structure_counts_coo: bad shape");
+  cudaStream_t st = as_stream(stream);
+  const int C = num_classes;
+  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
+  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
+  if (n == 0) return 0;
+  WDGH_CUDA(cudaMemsetAsync(deg_nsl, 0, n * sizeof(int32_t), st));
+  WDGH_CUDA(cudaMemsetAsync(match_nsl, 0, n * sizeof(int32_t), st));
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
+  const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
+  if (num_edges > 0) {
+    structure_coo_kernel<<<persistent_grid(ceil_div(num_edges, 256), 8), 256, hist_smem, st>>>(
+        edge_index, num_edges, n, labels, C, cnt, deg_nsl, match_nsl);
+    WDGH_LAUNCHED("structure_coo_kernel");
+  }
+  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
+  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(nullptr, n, labels, C, deg_nsl,
+                                                                                     match_nsl, cnt, node_sum);
+  WDGH_LAUNCHED("structure_nodes_kernel");
+  return 0;
+}
+
+extern "C" int wdgh_edge_label_rows_equal(const int64_t *rowptr, const int32_t *col, int64_t n,
+                                          const float *label_rows, int64_t c, int64_t ld,
+                                          unsigned long long *equal_count, void *stream) {
+  WDGH_REQUIRE(rowptr && label_rows && equal_count && n >= 0 && c >= 1 && ld >= c,
+               "wdgh_edge_label_rows_equal: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  WDGH_CUDA(cudaMemsetAsync(equal_count, 0, sizeof(unsigned long long), st));
+  if (n == 0) return 0;
+  label_rows_equal_kernel<<<persistent_grid(ceil_div(n, 8), 8), 256, 0, st>>>(rowptr, col, n, label_rows, c, ld,
+                                                                             equal_count);
+  WDGH_LAUNCHED("label_rows_equal_kernel");
+  return 0;
+}

@@ -1,0 +1,353 @@
+"""HBM-resident CSR graph + thin typed wrappers over the C ABI (include/wdgh_b200.h).
+
+torch is used for device memory, streams and dtype plumbing only; every
+arithmetic step on the path is a kernel of libwdgh_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NORM_NONE, NORM_RW, NORM_SYM, check, lib, ptr, stream_ptr
+
+HEAVY_THRESHOLD = 512  # entries; longer rows are split into chunks of this many (degree binning)
+
+
+def _dev():
+    _lib.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _cuda(t, dtype=None):
+    """Move to the current CUDA device (plumbing), contiguous, optional dtype."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    if t.device.type != "cuda":
+        t = t.to(_dev(), non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class CSRGraph:
+    """Adjacency in CSR (rowptr int64, col int32, optional float32 values), resident in HBM.
+
+    Row-major order with sorted columns -- the order `A.coalesce().indices()` produces,
+    which every reference metric starts from (utils/homophily_metrics.py:50,63,127,165).
+    """
+
+    def __init__(self, rowptr, col, val, n, threshold=HEAVY_THRESHOLD):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n, self.nnz = int(n), int(col.shape[0])
+        self.threshold = int(threshold)
+        self.device = rowptr.device
+        self._plan = None
+        self._rows = None
+        self._dinv = {}
+        self._counts = {}
+
+    # ---- constructors ----------------------------------------------------
+    @classmethod
+    def from_coo_indices(cls, indices, values, n, threshold=HEAVY_THRESHOLD):
+        """indices: int64 [2, nnz], coalesced (row-major sorted, unique)."""
+        dev = _dev()
+        indices = _cuda(indices, torch.int64)
+        nnz = int(indices.shape[1])
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        check(lib.wdgh_coo_to_csr(ptr(indices), nnz, n, ptr(rowptr), ptr(col), stream_ptr()), "wdgh_coo_to_csr")
+        val = None if values is None else _cuda(values, torch.float32)
+        g = cls(rowptr, col, val, n, threshold)
+        g._indices = indices
+        return g
+
+    @classmethod
+    def from_torch_sparse(cls, a, threshold=HEAVY_THRESHOLD, binary=False):
+        """a: torch sparse COO tensor (any device).  Coalesced first if it is not (torch plumbing)."""
+        if not a.is_sparse:
+            raise TypeError("expected a torch sparse COO tensor")
+        if a.device.type != "cuda":
+            a = a.to(_dev())
+        a = a.coalesce()
+        vals = None if binary else a.values()
+        return cls.from_coo_indices(a.indices(), vals, a.shape[0], threshold)
+
+    @classmethod
+    def from_scipy(cls, m, threshold=HEAVY_THRESHOLD, binary=False):
+        m = m.tocsr()
+        m.sum_duplicates()
+        m.sort_indices()
+        dev = _dev()
+        rowptr = torch.from_numpy(m.indptr.astype(np.int64)).to(dev)
+        col = torch.from_numpy(m.indices.astype(np.int32)).to(dev)
+        val = None if binary else torch.from_numpy(m.data.astype(np.float32)).to(dev)
+        return cls(rowptr, col, val, m.shape[0], threshold)
+
+    @classmethod
+    def from_csr(cls, rowptr, col, val, n, threshold=HEAVY_THRESHOLD):
+        return cls(_cuda(rowptr, torch.int64), _cuda(col, torch.int32),
+                   None if val is None else _cuda(val, torch.float32), n, threshold)
+
+    # ---- derived data ----------------------------------------------------
+    @property
+    def plan(self):
+        """(device plan tensor, host int64[4] ctypes array) -- built once per graph."""
+        if self._plan is None:
+            cap = 2 * self.nnz // self.threshold + 2
+            plan = torch.empty(_lib.PLAN_HEADER + 3 * cap, dtype=torch.int64, device=self.device)
+            host = (C.c_int64 * 4)()
+            check(lib.wdgh_plan_build(ptr(self.rowptr), self.n, self.threshold, ptr(plan), cap, host, stream_ptr()),
+                  "wdgh_plan_build")
+            self._plan = (plan, host)
+        return self._plan
+
+    @property
+    def n_chunks(self):
+        return int(self.plan[1][1])
+
+    @property
+    def n_heavy(self):
+        return int(self.plan[1][0])
+
+    def rows(self):
+        """int64 row id of every stored entry (COO view)."""
+        if self._rows is None:
+            r = torch.empty(self.nnz, dtype=torch.int64, device=self.device)
+            check(lib.wdgh_csr_to_coo_rows(ptr(self.rowptr), self.n, self.nnz, ptr(r), stream_ptr()),
+                  "wdgh_csr_to_coo_rows")
+            self._rows = r
+        return self._rows
+
+    def indices(self):
+        """torch-style int64 [2, nnz] index tensor."""
+        return torch.stack([self.rows(), self.col.to(torch.int64)])
+
+    def degree_scale(self, norm, self_loop, want64=False):
+        key = (norm, bool(self_loop), want64)
+        if key not in self._dinv:
+            dinv = torch.empty(self.n, dtype=torch.float32, device=self.device)
+            d64 = torch.empty(self.n, dtype=torch.float64, device=self.device) if want64 else None
+            check(lib.wdgh_degree_scale(ptr(self.rowptr), ptr(self.val), self.n, norm, int(bool(self_loop)),
+                                        ptr(dinv), ptr(d64), stream_ptr()), "wdgh_degree_scale")
+            self._dinv[key] = (dinv, d64)
+        return self._dinv[key]
+
+    def with_self_loops(self):
+        """CSR of A + I (diagonal merged or inserted), util_funcs.py:385,420."""
+        dev = self.device
+        n, nnz = self.n, self.nnz
+        out_rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        out_col = torch.empty(nnz + n, dtype=torch.int32, device=dev)
+        out_val = torch.empty(nnz + n, dtype=torch.float32, device=dev)
+        scratch = torch.empty(n + 2 * ((n + 1023) // 1024) + 8, dtype=torch.int64, device=dev)
+        check(lib.wdgh_add_self_loops(ptr(self.rowptr), ptr(self.col), ptr(self.val), n, ptr(out_rowptr),
+                                      ptr(out_col), ptr(out_val), ptr(scratch), stream_ptr()), "wdgh_add_self_loops")
+        new_nnz = int(out_rowptr[-1].item())
+        return CSRGraph(out_rowptr, out_col[:new_nnz], out_val[:new_nnz], n, self.threshold)
+
+    def normalized(self, norm):
+        """Materialised D^-1/2 A D^-1/2 (SYM) or D^-1 A (RW) of THIS matrix (no self-loop added)."""
+        _, d64 = self.degree_scale(norm, False, want64=True)
+        out = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
+        check(lib.wdgh_scale_values(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n, norm, ptr(d64), ptr(out),
+                                    stream_ptr()), "wdgh_scale_values")
+        g = CSRGraph(self.rowptr, self.col, out, self.n, self.threshold)
+        g._plan, g._rows = self._plan, self._rows
+        return g
+
+    def to_torch_sparse(self):
+        v = self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32, device=self.device)
+        return torch.sparse_coo_tensor(self.indices(), v, (self.n, self.n), is_coalesced=True)
+
+
+# ---------------------------------------------------------------------------
+# A_hat X aggregation
+# ---------------------------------------------------------------------------
+def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None):
+    """y = norm(A [+I]) x in float32 on the GPU (hm.py:192,199,234; util_funcs.py:383-390,418-426)."""
+    x = _cuda(x, torch.float32)
+    if x.dim() != 2 or x.shape[0] != g.n:
+        raise ValueError(f"features must be [n={g.n}, d], got {tuple(x.shape)}")
+    d = int(x.shape[1])
+    y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=g.device)
+    plan, plan_host = g.plan
+    ldp = (d + 3) & ~3
+    partial = torch.empty(g.n_chunks * ldp, dtype=torch.float32, device=g.device) if g.n_chunks else None
+    dinv = g.degree_scale(norm, add_self_loop)[0] if norm != NORM_NONE else None
+    check(lib.wdgh_spmm_csr(ptr(g.rowptr), ptr(g.col), ptr(g.val), g.n, ptr(x), d, x.stride(0), ptr(y), y.stride(0),
+                            norm, int(bool(add_self_loop)), ptr(dinv), ptr(plan), plan_host, ptr(partial),
+                            stream_ptr()), "wdgh_spmm_csr")
+    return y
+
+
+# ---------------------------------------------------------------------------
+# label statistics
+# ---------------------------------------------------------------------------
+@dataclass
+class StructureCounts:
+    """Exact integer statistics of one (graph, labels) pair (see include/wdgh_b200.h)."""
+    n: int
+    nnz: int
+    num_classes: int
+    match_all: int
+    match_lab: int
+    n_lab: int
+    n_self: int
+    n_empty: int
+    nbins: int
+    n_nodes_nsl: int
+    class_count: np.ndarray   # [C] int64
+    class_deg: np.ndarray     # [C] int64, sum of stored entries per row over the class
+    hist: np.ndarray          # [C, C] int64
+    node_sum: float           # sum_i f32(match_i)/f32(deg_i)
+    deg_nsl: torch.Tensor     # [n] int32 (device)
+    match_nsl: torch.Tensor   # [n] int32 (device)
+
+
+def pack_labels(labels):
+    """int64 label tensor -> (int32 device tensor, max label)."""
+    labels = _cuda(labels).reshape(-1)
+    if labels.dtype != torch.int64:
+        labels = labels.to(torch.int64)
+    n = labels.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=labels.device)
+    mx = torch.empty(1, dtype=torch.int32, device=labels.device)
+    check(lib.wdgh_pack_labels(ptr(labels), n, ptr(out), ptr(mx), stream_ptr()), "wdgh_pack_labels")
+    return out, int(mx.item())
+
+
+def _unpack_counts(n, nnz, c, counters, node_sum, deg, match):
+    h = counters.cpu().numpy()
+    H = _lib.SC_HEADER
+    return StructureCounts(
+        n=n, nnz=nnz, num_classes=c,
+        match_all=int(h[_lib.SC_MATCH_ALL]), match_lab=int(h[_lib.SC_MATCH_LAB]), n_lab=int(h[_lib.SC_N_LAB]),
+        n_self=int(h[_lib.SC_N_SELF]), n_empty=int(h[_lib.SC_N_EMPTY]), nbins=int(h[_lib.SC_NBINS]),
+        n_nodes_nsl=int(h[_lib.SC_N_NODES_NSL]),
+        class_count=h[H:H + c].copy(), class_deg=h[H + c:H + 2 * c].copy(),
+        hist=h[H + 2 * c:H + 2 * c + c * c].reshape(c, c).copy(),
+        node_sum=float(node_sum.item()), deg_nsl=deg, match_nsl=match)
+
+
+def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
+    c = int(num_classes)
+    dev = g.device
+    counters = torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev)
+    node_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    deg = torch.empty(g.n, dtype=torch.int32, device=dev)
+    match = torch.empty(g.n, dtype=torch.int32, device=dev)
+    plan, plan_host = g.plan
+    check(lib.wdgh_structure_counts(ptr(g.rowptr), ptr(g.col), g.n, g.nnz, ptr(labels32), c, ptr(plan), plan_host,
+                                    ptr(counters), ptr(node_sum), ptr(deg), ptr(match), stream_ptr()),
+          "wdgh_structure_counts")
+    return _unpack_counts(g.n, g.nnz, c, counters, node_sum, deg, match)
+
+
+def structure_counts_coo(edge_index, n, labels32, num_classes) -> StructureCounts:
+    ei = _cuda(edge_index, torch.int64)
+    c = int(num_classes)
+    e = int(ei.shape[1])
+    dev = ei.device
+    counters = torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev)
+    node_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    deg = torch.empty(n, dtype=torch.int32, device=dev)
+    match = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.wdgh_structure_counts_coo(ptr(ei), e, n, ptr(labels32), c, ptr(counters), ptr(node_sum), ptr(deg),
+                                        ptr(match), stream_ptr()), "wdgh_structure_counts_coo")
+    return _unpack_counts(n, e, c, counters, node_sum, deg, match)
+
+
+def edge_label_rows_equal(g: CSRGraph, label_rows) -> int:
+    lab = _cuda(label_rows, torch.float32)
+    out = torch.empty(1, dtype=torch.int64, device=g.device)
+    check(lib.wdgh_edge_label_rows_equal(ptr(g.rowptr), ptr(g.col), g.n, ptr(lab), lab.shape[1], lab.stride(0),
+                                         ptr(out), stream_ptr()), "wdgh_edge_label_rows_equal")
+    return int(out.item())
+
+
+def edge_cosine(g: CSRGraph, x, entry_ids=None):
+    """(sum of cosines, entries counted): all off-diagonal positive entries, or the listed entry ids."""
+    x = _cuda(x, torch.float32)
+    s = torch.empty(1, dtype=torch.float64, device=g.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=g.device)
+    if entry_ids is None:
+        mode, ids, n_ids = 0, None, g.nnz
+    else:
+        ids = _cuda(entry_ids, torch.int64)
+        mode, n_ids = 1, int(ids.shape[0])
+    check(lib.wdgh_edge_cosine(ptr(g.rowptr), ptr(g.col), ptr(g.val), g.n, ptr(x), x.shape[1], x.stride(0), mode,
+                               ptr(ids), n_ids, ptr(s), ptr(cnt), stream_ptr()), "wdgh_edge_cosine")
+    return float(s.item()), int(cnt.item())
+
+
+# ---------------------------------------------------------------------------
+# dense contractions
+# ---------------------------------------------------------------------------
+USE_TENSOR_CORES = False  # flipped to True once gram_tc.cu is validated on the B200
+
+
+def gather_rows(x, ids):
+    x = _cuda(x, torch.float32)
+    ids = _cuda(ids, torch.int64)
+    m, d = int(ids.shape[0]), int(x.shape[1])
+    out = torch.empty((m, d), dtype=torch.float32, device=x.device)
+    check(lib.wdgh_gather_rows(ptr(x), d, x.stride(0), ptr(ids), m, ptr(out), d, stream_ptr()), "wdgh_gather_rows")
+    return out
+
+
+def gram(z, use_tensor_cores=None):
+    """g = z z^T (float32)."""
+    z = _cuda(z, torch.float32)
+    m, d = int(z.shape[0]), int(z.shape[1])
+    g = torch.empty((m, m), dtype=torch.float32, device=z.device)
+    tc = USE_TENSOR_CORES if use_tensor_cores is None else use_tensor_cores
+    check(lib.wdgh_gram(ptr(z), m, d, z.stride(0), ptr(g), m, int(bool(tc)), stream_ptr()), "wdgh_gram")
+    return g
+
+
+def class_colsum(gm, labels32, num_classes, is_mean=False):
+    m = int(gm.shape[0])
+    w = torch.empty((m, num_classes), dtype=torch.float32, device=gm.device)
+    check(lib.wdgh_class_colsum(ptr(gm), m, gm.stride(0), ptr(labels32), num_classes, int(bool(is_mean)), ptr(w),
+                                stream_ptr()), "wdgh_class_colsum")
+    return w
+
+
+def las_count(w, labels32, label_rows, hard, lp, is_sum) -> int:
+    m, c = int(w.shape[0]), int(w.shape[1])
+    label_rows = _cuda(label_rows, torch.float32)
+    scratch = torch.empty(c, dtype=torch.float32, device=w.device)
+    cnt = torch.empty(1, dtype=torch.int64, device=w.device)
+    check(lib.wdgh_las_score(ptr(w), ptr(labels32), ptr(label_rows), m, c, int(bool(hard)), int(lp), int(bool(is_sum)),
+                             ptr(scratch), ptr(cnt), stream_ptr()), "wdgh_las_score")
+    return int(cnt.item())
+
+
+def gntk_transform_(gm, n_layers):
+    m = int(gm.shape[0])
+    scratch = torch.empty(m, dtype=torch.float32, device=gm.device)
+    check(lib.wdgh_gntk_transform(ptr(gm), m, gm.stride(0), int(n_layers), ptr(scratch), stream_ptr()),
+          "wdgh_gntk_transform")
+    return gm
+
+
+def argmax_rows(m):
+    m = _cuda(m, torch.float32)
+    out = torch.empty(m.shape[0], dtype=torch.int32, device=m.device)
+    check(lib.wdgh_argmax_rows(ptr(m), m.shape[0], m.shape[1], m.stride(0), ptr(out), stream_ptr()),
+          "wdgh_argmax_rows")
+    return out
+
+
+def normalize_dense(x, symmetric=0):
+    x = _cuda(x, torch.float32)
+    n, d = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(n, dtype=torch.float32, device=x.device)
+    check(lib.wdgh_normalize_dense(ptr(x), n, d, x.stride(0), int(symmetric), ptr(scratch), ptr(out), d,
+                                   stream_ptr()), "wdgh_normalize_dense")
+    return out
