@@ -104,11 +104,15 @@ int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
  *   dinv     : float32[n] from wdgh_degree_scale (required iff norm != NONE)
  *   plan_i64 / plan_host : from wdgh_plan_build (required)
  *   partial  : float32[n_chunks * roundup(d,4)] scratch for split rows (may be NULL if n_chunks == 0)
+ *   row_offset : 0 for a whole graph.  For a 1-D row shard (multi-GPU) the CSR holds rows
+ *              [row_offset, row_offset + n) of the global matrix: `col`, `x` and `dinv` use global
+ *              node ids, `y` is local ([n][d]).
  * Replaces torch.spmm / torch.mm(adj, features) at hm.py:192,199,234,299,315. */
 int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                   const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                   int norm, int add_self_loop, const float *dinv,
-                  const int64_t *plan_i64, const int64_t *plan_host, float *partial, void *stream);
+                  const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                  int64_t row_offset, void *stream);
 
 /* ---- label metrics: one pass over the edges ------------------------------ */
 /* Integer statistics every label metric of homophily_metrics.py is a ratio of
@@ -139,7 +143,9 @@ int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, 
                           const int32_t *labels, int32_t num_classes,
                           const int64_t *plan_i64, const int64_t *plan_host,
                           int64_t *counters, double *node_sum,
-                          int32_t *deg_nsl, int32_t *match_nsl, void *stream);
+                          int32_t *deg_nsl, int32_t *match_nsl,
+                          int64_t row_offset /* as in wdgh_spmm_csr: labels are global, deg/match local */,
+                          void *stream);
 /* Same statistics from an arbitrary edge list (torch `edge_index` int64[2][E]: unsorted, repeats
  * counted with multiplicity), as node_homophily_edge_idx / compact_matrix_edge_idx / our_measure
  * receive it (hm.py:71,81,105).  Row lengths are unknown here, so the per-class degree mass

@@ -6,7 +6,7 @@
 
 extern "C" int wdgh_spmm_csr(const int64_t *, const int32_t *, const float *, int64_t, const float *, int64_t,
                              int64_t, float *, int64_t, int, int, const float *, const int64_t *, const int64_t *,
-                             float *, void *);
+                             float *, int64_t, void *);
 
 namespace wdgh {
 
@@ -85,10 +85,10 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     if (rc) return rc;
   }
   rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x, d, d, c.y, d, norm, add_self_loop,
-                     norm != WDGH_NORM_NONE ? c.dinv : nullptr, c.plan, plan_host, c.partial, st);
+                     norm != WDGH_NORM_NONE ? c.dinv : nullptr, c.plan, plan_host, c.partial, 0, st);
   if (rc) return rc;
   rc = wdgh_structure_counts(c.rowptr, c.col, n, nnz, c.labels, C, c.plan, plan_host, c.counters, c.node_sum, c.deg,
-                             c.match, st);
+                             c.match, 0, st);
   if (rc) return rc;
   WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256)
 spmm_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                  const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
                  float *__restrict__ y, int64_t ldy, int norm, int self_loop, const float *__restrict__ dinv,
-                 int64_t threshold) {
+                 int64_t threshold, int64_t row_offset) {
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
@@ -127,7 +127,8 @@ spmm_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__
   for (int t = 0; t < NCH; ++t) acc[t].zero();
   accumulate_range<G, VEC, NCH, HAS_VAL>(acc, s, e, col, val, norm == WDGH_NORM_SYM ? dinv : nullptr, x, ldx,
                                          cbase, d, gl, gmask);
-  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + row) : 1.f;
+  const int64_t grow = row + row_offset;  // id of this row in the global (column) index space
+  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
   const float self_w = (norm == WDGH_NORM_SYM) ? si : 1.f;
 #pragma unroll
   for (int t = 0; t < NCH; ++t) {
@@ -135,7 +136,7 @@ spmm_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__
     if (c < d) {
       if (self_loop) {
         Vec<VEC> xi;
-        xi.load(x + row * ldx + c);
+        xi.load(x + grow * ldx + c);
         acc[t].fma(self_w, xi);
       }
       acc[t].scale(si);
@@ -179,19 +180,20 @@ __global__ void __launch_bounds__(128)
 spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__restrict__ x, int d, int64_t ldx,
                          float *__restrict__ y, int64_t ldy, int norm, int self_loop,
                          const float *__restrict__ dinv, const int64_t *__restrict__ plan,
-                         const float *__restrict__ partial, int64_t ldp) {
+                         const float *__restrict__ partial, int64_t ldp, int64_t row_offset) {
   const int64_t k = blockIdx.x;
   const int64_t cap = plan[kPlanCapacity], T = plan[kPlanThreshold];
   const int64_t row = plan_heavy_row(plan)[k];
   const int64_t c0 = plan_heavy_chunk0(plan, cap)[k];
   const int64_t deg = __ldg(rowptr + row + 1) - __ldg(rowptr + row);
   const int64_t nch = (deg + T - 1) / T;
-  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + row) : 1.f;
+  const int64_t grow = row + row_offset;
+  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
   const float self_w = (norm == WDGH_NORM_SYM) ? si : 1.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float acc = 0.f;
     for (int64_t p = 0; p < nch; ++p) acc += partial[(c0 + p) * ldp + c];
-    if (self_loop) acc = fmaf(self_w, __ldg(x + row * ldx + c), acc);
+    if (self_loop) acc = fmaf(self_w, __ldg(x + grow * ldx + c), acc);
     y[row * ldy + c] = acc * si;
   }
 }
@@ -209,7 +211,7 @@ struct SpmmArgs {
   int norm, self_loop;
   const float *dinv;
   const int64_t *plan;
-  int64_t threshold, n_heavy, n_chunks;
+  int64_t threshold, n_heavy, n_chunks, row_offset;
   float *partial;
   int64_t ldp;
   cudaStream_t st;
@@ -222,7 +224,8 @@ static int launch_rows(const SpmmArgs &a) {
   const int tile = G * VEC * NCH;
   dim3 grid((unsigned)ceil_div(a.n, rows_per_cta), (unsigned)ceil_div(a.d, tile));
   spmm_rows_kernel<G, VEC, NCH, HAS_VAL><<<grid, 256, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y,
-                                                                a.ldy, a.norm, a.self_loop, a.dinv, a.threshold);
+                                                                a.ldy, a.norm, a.self_loop, a.dinv, a.threshold,
+                                                                a.row_offset);
   WDGH_LAUNCHED("spmm_rows_kernel");
   return 0;
 }
@@ -236,7 +239,8 @@ static int launch_heavy(const SpmmArgs &a) {
                                                                a.dinv, a.plan, a.n_chunks, a.partial, a.ldp);
   WDGH_LAUNCHED("spmm_chunks_kernel");
   spmm_heavy_finish_kernel<<<(unsigned)a.n_heavy, 128, 0, a.st>>>(a.rowptr, a.x, a.d, a.ldx, a.y, a.ldy, a.norm,
-                                                                  a.self_loop, a.dinv, a.plan, a.partial, a.ldp);
+                                                                  a.self_loop, a.dinv, a.plan, a.partial, a.ldp,
+                                                                  a.row_offset);
   WDGH_LAUNCHED("spmm_heavy_finish_kernel");
   return 0;
 }
@@ -280,18 +284,20 @@ using namespace wdgh;
 extern "C" int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                              const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy, int norm,
                              int add_self_loop, const float *dinv, const int64_t *plan_i64,
-                             const int64_t *plan_host, float *partial, void *stream) {
-  WDGH_REQUIRE(rowptr && col && x && y && plan_i64 && plan_host, "wdgh_spmm_csr: null pointer");
+                             const int64_t *plan_host, float *partial, int64_t row_offset, void *stream) {
+  WDGH_REQUIRE(rowptr && x && y && plan_i64 && plan_host, "wdgh_spmm_csr: null pointer");  // col may be NULL iff nnz == 0
   WDGH_REQUIRE(n >= 0 && d > 0 && d <= (1 << 24) && ldx >= d && ldy >= d, "wdgh_spmm_csr: bad shape");
   WDGH_REQUIRE(norm == WDGH_NORM_NONE || norm == WDGH_NORM_RW || norm == WDGH_NORM_SYM, "wdgh_spmm_csr: bad norm");
   WDGH_REQUIRE(norm == WDGH_NORM_NONE || dinv != nullptr, "wdgh_spmm_csr: norm requires dinv");
   WDGH_REQUIRE(x != y, "wdgh_spmm_csr: in-place aggregation is not supported");
+  WDGH_REQUIRE(row_offset >= 0, "wdgh_spmm_csr: negative row_offset");
   if (n == 0) return 0;
   SpmmArgs a;
   a.rowptr = rowptr; a.col = col; a.val = val; a.n = n; a.x = x; a.d = (int)d; a.ldx = ldx; a.y = y; a.ldy = ldy;
   a.norm = norm; a.self_loop = add_self_loop ? 1 : 0; a.dinv = dinv; a.plan = plan_i64;
   a.n_heavy = plan_host[0]; a.n_chunks = plan_host[1]; a.threshold = plan_host[2];
   a.partial = partial; a.ldp = (d + 3) & ~int64_t(3);
+  a.row_offset = row_offset;
   a.st = as_stream(stream);
   WDGH_REQUIRE(a.n_chunks == 0 || partial != nullptr, "wdgh_spmm_csr: split rows need the partial buffer");
   const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256)
 structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
                       const int32_t *__restrict__ labels, int C, int64_t threshold,
                       unsigned long long *__restrict__ counters, int32_t *__restrict__ deg_nsl,
-                      int32_t *__restrict__ match_nsl) {
+                      int32_t *__restrict__ match_nsl, int64_t row_offset) {
   extern __shared__ unsigned s_hist[];
   const bool use_smem = (C * C <= kHistSmemBins);
   unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
@@ -87,7 +87,7 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
       e = __ldg(rowptr + row + 1);
       mine = (e - s) <= threshold;
       if (!mine) e = s;
-      li = __ldg(labels + row);
+      li = __ldg(labels + row + row_offset);
     }
     const int iters = warp_max((int)((e - s + G - 1) / G));
     int m_nsl = 0, d_nsl = 0;
@@ -97,7 +97,7 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
       if (idx < e) {
         const int j = __ldg(col + idx);
         const int lj = __ldg(labels + j);
-        visit(row, li, j, lj, C, acc, m_nsl, d_nsl, key);
+        visit(row + row_offset, li, j, lj, C, acc, m_nsl, d_nsl, key);
       }
       fold_keys(key, s_hist, g_hist, use_smem);
     }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                         const int32_t *__restrict__ labels, int C, const int64_t *__restrict__ plan,
                         int64_t n_chunks, unsigned long long *__restrict__ counters,
-                        int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl) {
+                        int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl, int64_t row_offset) {
   extern __shared__ unsigned s_hist[];
   const bool use_smem = (C * C <= kHistSmemBins);
   unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
@@ -144,7 +144,7 @@ structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
     const int64_t part = chunk - plan_heavy_chunk0(plan, cap)[k];
     const int64_t s = __ldg(rowptr + row) + part * T;
     const int64_t e = min(s + T, __ldg(rowptr + row + 1));
-    const int li = __ldg(labels + row);
+    const int li = __ldg(labels + row + row_offset);
     int m_nsl = 0, d_nsl = 0;
     for (int64_t base = s; base < e; base += 32) {  // warp-uniform trip count
       const int64_t idx = base + lane;
@@ -152,7 +152,7 @@ structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
       if (idx < e) {
         const int j = __ldg(col + idx);
         const int lj = __ldg(labels + j);
-        visit(row, li, j, lj, C, acc, m_nsl, d_nsl, key);
+        visit(row + row_offset, li, j, lj, C, acc, m_nsl, d_nsl, key);
       }
       fold_keys(key, s_hist, g_hist, use_smem);
     }
@@ -217,7 +217,8 @@ structure_coo_kernel(const int64_t *__restrict__ edge_index, int64_t E, int64_t 
 __global__ void __launch_bounds__(256)
 structure_nodes_kernel(const int64_t *__restrict__ rowptr, int64_t n, const int32_t *__restrict__ labels, int C,
                        const int32_t *__restrict__ deg_nsl, const int32_t *__restrict__ match_nsl,
-                       unsigned long long *__restrict__ counters, double *__restrict__ node_sum) {
+                       unsigned long long *__restrict__ counters, double *__restrict__ node_sum,
+                       int64_t row_offset) {
   extern __shared__ unsigned long long s_cls[];  // [C] class_count, [C] class_deg
   const bool use_smem = (C <= 2048);
   unsigned long long *g_cls = counters + WDGH_SC_HEADER;
@@ -235,10 +236,10 @@ structure_nodes_kernel(const int64_t *__restrict__ rowptr, int64_t n, const int3
     if (d > 0) {
       sum += (double)((float)m / (float)d);  // float32 division as torch does (hm.py:77)
       n_nsl += 1;
-      nbins = i + 1;  // i is increasing per thread
+      nbins = i + row_offset + 1;  // i is increasing per thread
     }
     if (deg_all == 0) n_empty += 1;
-    const int l = labels[i];
+    const int l = labels[i + row_offset];
     if (l >= 0 && l < C) {
       atomicAdd(&cls[l], 1ull);
       if (rowptr) atomicAdd(&cls[C + l], (unsigned long long)deg_all);
@@ -286,10 +287,10 @@ label_rows_equal_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
 template <int G>
 static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels, int C,
                        int64_t threshold, unsigned long long *counters, int32_t *deg, int32_t *match,
-                       size_t smem, cudaStream_t st) {
+                       size_t smem, cudaStream_t st, int64_t row_offset) {
   const int64_t ctas = ceil_div(n, (int64_t)8 * (32 / G));
   structure_rows_kernel<G><<<persistent_grid(ctas, 8), 256, smem, st>>>(rowptr, col, n, labels, C, threshold, counters,
-                                                                       deg, match);
+                                                                       deg, match, row_offset);
   WDGH_LAUNCHED("structure_rows_kernel");
   return 0;
 }
@@ -301,7 +302,7 @@ using namespace wdgh;
 extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                                      const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
                                      const int64_t *plan_host, int64_t *counters, double *node_sum,
-                                     int32_t *deg_nsl, int32_t *match_nsl, void *stream) {
+                                     int32_t *deg_nsl, int32_t *match_nsl, int64_t row_offset, void *stream) {
   WDGH_REQUIRE(rowptr && labels && plan_i64 && plan_host && counters && node_sum && deg_nsl && match_nsl,
                "wdgh_structure_counts: null pointer");
   WDGH_REQUIRE(n >= 0 && nnz >= 0 && (col || nnz == 0), "wdgh_structure_counts: bad shape");
@@ -317,19 +318,19 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   const int64_t threshold = plan_host[2], n_chunks = plan_host[1];
   const double avg = (double)nnz / (double)n;
   int rc;
-  if (avg <= 6.0) rc = launch_rows<4>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
-  else if (avg <= 12.0) rc = launch_rows<8>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
-  else if (avg <= 24.0) rc = launch_rows<16>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
-  else rc = launch_rows<32>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st);
+  if (avg <= 6.0) rc = launch_rows<4>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else if (avg <= 12.0) rc = launch_rows<8>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else if (avg <= 24.0) rc = launch_rows<16>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else rc = launch_rows<32>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
   if (rc) return rc;
   if (n_chunks > 0) {
     structure_chunks_kernel<<<persistent_grid(ceil_div(n_chunks, 8), 8), 256, hist_smem, st>>>(
-        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl);
+        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl, row_offset);
     WDGH_LAUNCHED("structure_chunks_kernel");
   }
   const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
   structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
-                                                                                     match_nsl, cnt, node_sum);
+                                                                                     match_nsl, cnt, node_sum, row_offset);
   WDGH_LAUNCHED("structure_nodes_kernel");
   return 0;
 }
@@ -358,7 +359,7 @@ extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_
   }
   const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
   structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(nullptr, n, labels, C, deg_nsl,
-                                                                                     match_nsl, cnt, node_sum);
+                                                                                     match_nsl, cnt, node_sum, 0);
   WDGH_LAUNCHED("structure_nodes_kernel");
   return 0;
 }

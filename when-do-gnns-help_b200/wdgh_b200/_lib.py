@@ -40,8 +40,8 @@ SIGNATURES = {
     "wdgh_scale_values": [_p, _p, _p, _i64, _int, _p, _p, _p],
     "wdgh_add_self_loops": [_p, _p, _p, _i64, _p, _p, _p, _p, _p],
     "wdgh_normalize_dense": [_p, _i64, _i64, _i64, _int, _p, _p, _i64, _p],
-    "wdgh_spmm_csr": [_p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, C.POINTER(_i64), _p, _p],
-    "wdgh_structure_counts": [_p, _p, _i64, _i64, _p, _i32, _p, C.POINTER(_i64), _p, _p, _p, _p, _p],
+    "wdgh_spmm_csr": [_p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, C.POINTER(_i64), _p, _i64, _p],
+    "wdgh_structure_counts": [_p, _p, _i64, _i64, _p, _i32, _p, C.POINTER(_i64), _p, _p, _p, _p, _i64, _p],
     "wdgh_structure_counts_coo": [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p],
     "wdgh_edge_label_rows_equal": [_p, _p, _i64, _p, _i64, _i64, _p, _p],
     "wdgh_edge_cosine": [_p, _p, _p, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p],

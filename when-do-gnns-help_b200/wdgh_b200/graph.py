@@ -40,9 +40,12 @@ class CSRGraph:
     which every reference metric starts from (utils/homophily_metrics.py:50,63,127,165).
     """
 
-    def __init__(self, rowptr, col, val, n, threshold=HEAVY_THRESHOLD):
+    def __init__(self, rowptr, col, val, n, threshold=HEAVY_THRESHOLD, row_offset=0, n_global=None):
         self.rowptr, self.col, self.val = rowptr, col, val
         self.n, self.nnz = int(n), int(col.shape[0])
+        # a 1-D row shard holds rows [row_offset, row_offset + n) of an n_global x n_global matrix
+        self.row_offset = int(row_offset)
+        self.n_global = int(n_global) if n_global is not None else int(n)
         self.threshold = int(threshold)
         self.device = rowptr.device
         self._plan = None
@@ -167,20 +170,25 @@ class CSRGraph:
 # ---------------------------------------------------------------------------
 # A_hat X aggregation
 # ---------------------------------------------------------------------------
-def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None):
-    """y = norm(A [+I]) x in float32 on the GPU (hm.py:192,199,234; util_funcs.py:383-390,418-426)."""
+def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=None):
+    """y = norm(A [+I]) x in float32 on the GPU (hm.py:192,199,234; util_funcs.py:383-390,418-426).
+
+    For a row shard `x` (and `dinv`, the all-gathered degree scale) are global, the result is local."""
     x = _cuda(x, torch.float32)
-    if x.dim() != 2 or x.shape[0] != g.n:
-        raise ValueError(f"features must be [n={g.n}, d], got {tuple(x.shape)}")
+    if x.dim() != 2 or x.shape[0] < g.n_global or (x.shape[0] != g.n_global and g.n_global == g.n):
+        raise ValueError(f"features must be [n={g.n_global}, d], got {tuple(x.shape)}")
     d = int(x.shape[1])
     y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=g.device)
     plan, plan_host = g.plan
     ldp = (d + 3) & ~3
     partial = torch.empty(g.n_chunks * ldp, dtype=torch.float32, device=g.device) if g.n_chunks else None
-    dinv = g.degree_scale(norm, add_self_loop)[0] if norm != NORM_NONE else None
+    if norm != NORM_NONE and dinv is None:
+        if g.n_global != g.n:
+            raise ValueError("a row shard needs the all-gathered degree scale (dinv=...)")
+        dinv = g.degree_scale(norm, add_self_loop)[0]
     check(lib.wdgh_spmm_csr(ptr(g.rowptr), ptr(g.col), ptr(g.val), g.n, ptr(x), d, x.stride(0), ptr(y), y.stride(0),
                             norm, int(bool(add_self_loop)), ptr(dinv), ptr(plan), plan_host, ptr(partial),
-                            stream_ptr()), "wdgh_spmm_csr")
+                            g.row_offset, stream_ptr()), "wdgh_spmm_csr")
     return y
 
 
@@ -233,18 +241,28 @@ def _unpack_counts(n, nnz, c, counters, node_sum, deg, match):
         node_sum=float(node_sum.item()), deg_nsl=deg, match_nsl=match)
 
 
-def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
+def structure_counts_raw(g: CSRGraph, labels32, num_classes, scratch=None):
+    """Launch the label-statistics kernels; returns DEVICE tensors (counters, node_sum, deg, match), no sync.
+
+    `labels32` is indexed by global node id (length n_global for a row shard)."""
     c = int(num_classes)
     dev = g.device
-    counters = torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev)
-    node_sum = torch.empty(1, dtype=torch.float64, device=dev)
-    deg = torch.empty(g.n, dtype=torch.int32, device=dev)
-    match = torch.empty(g.n, dtype=torch.int32, device=dev)
+    if scratch is None:
+        scratch = (torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev),
+                   torch.empty(1, dtype=torch.float64, device=dev),
+                   torch.empty(g.n, dtype=torch.int32, device=dev),
+                   torch.empty(g.n, dtype=torch.int32, device=dev))
+    counters, node_sum, deg, match = scratch
     plan, plan_host = g.plan
     check(lib.wdgh_structure_counts(ptr(g.rowptr), ptr(g.col), g.n, g.nnz, ptr(labels32), c, ptr(plan), plan_host,
-                                    ptr(counters), ptr(node_sum), ptr(deg), ptr(match), stream_ptr()),
+                                    ptr(counters), ptr(node_sum), ptr(deg), ptr(match), g.row_offset, stream_ptr()),
           "wdgh_structure_counts")
-    return _unpack_counts(g.n, g.nnz, c, counters, node_sum, deg, match)
+    return counters, node_sum, deg, match
+
+
+def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
+    counters, node_sum, deg, match = structure_counts_raw(g, labels32, num_classes)
+    return _unpack_counts(g.n, g.nnz, int(num_classes), counters, node_sum, deg, match)
 
 
 def structure_counts_coo(edge_index, n, labels32, num_classes) -> StructureCounts:
