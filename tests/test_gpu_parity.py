@@ -356,7 +356,7 @@ def test_gram_vs_torch_fp64(W):
 def test_abi_rejects_bad_arguments(W):
     import ctypes as C
     lib = W._lib.lib
-    assert lib.wdgh_spmm_csr(None, None, None, 4, None, 4, 4, None, 4, 0, 0, None, None, None, None, None) == -1
+    assert lib.wdgh_spmm_csr(None, None, None, 4, None, 4, 4, None, 4, 0, 0, None, None, None, None, 0, None) == -1
     assert b"null pointer" in lib.wdgh_last_error()
     host = (C.c_int64 * 4)()
     assert lib.wdgh_plan_build(None, 4, 512, None, 4, host, None) == -1
