@@ -66,14 +66,18 @@ int wdgh_argmax_rows(const float *m, int64_t n, int64_t c, int64_t ld, int32_t *
  * many entries; everything else is handled one row per warp / sub-warp group.
  * The plan lives in caller-provided device memory and is reused by
  * wdgh_spmm_csr and wdgh_structure_counts for the same rowptr.
- *   plan_i64  : int64[WDGH_PLAN_HEADER + 3*capacity]   (device)
+ * The plan also records, for every "stream unit" of WDGH_UNIT consecutive stored entries, the row
+ * that contains the unit's first entry (the nnz-balanced SpMM walks units, not rows).
+ *   plan_i64  : int64[WDGH_PLAN_WORDS(capacity, nnz)]  (device)
  *   capacity  : >= 2 * nnz / heavy_threshold + 2       (upper bound on the number of chunks)
- *   plan_host : int64[4] HOST array the later calls take alongside plan_i64
+ *   plan_host : int64[8] HOST array the later calls take alongside plan_i64
  * SYNCHRONOUS (reads the two counters back to size the later launches). */
 #define WDGH_PLAN_HEADER 8
-int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t heavy_threshold,
+#define WDGH_UNIT 1024
+#define WDGH_PLAN_WORDS(capacity, nnz) (WDGH_PLAN_HEADER + 3 * (capacity) + ((nnz) + WDGH_UNIT - 1) / WDGH_UNIT)
+int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t nnz, int64_t heavy_threshold,
                     int64_t *plan_i64, int64_t capacity,
-                    int64_t *plan_host /* int64[4] out: n_heavy, n_chunks, threshold, capacity */,
+                    int64_t *plan_host /* int64[8] out: n_heavy, n_chunks, threshold, capacity, unit, n_units, nnz, 0 */,
                     void *stream);
 
 /* ---- normalisation (util_funcs.py:365-390, 418-426) ---------------------- */
@@ -81,7 +85,11 @@ int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t heavy_threshold,
  * of an all-zero row become 1 for SYM as in util_funcs.py:422.  val NULL = binary. */
 int wdgh_degree_scale(const int64_t *rowptr, const float *val, int64_t n,
                       int norm, int add_self_loop, float *dinv /* nullable */,
-                      double *dinv64 /* nullable: the same scale before the float32 cast */, void *stream);
+                      double *dinv64 /* nullable: the same scale before the float32 cast */,
+                      uint8_t *deg_code /* nullable, binary adjacency only: min(row length, 255) per node; lets
+                                           wdgh_spmm_csr replace the per-entry float gather by an L2-resident
+                                           1-byte lookup (255 = fall back to dinv) */,
+                      void *stream);
 /* Materialise the normalised values of a CSR that ALREADY contains its diagonal:
  * out[e] = f32( dinv64_i * val[e] * dinv64_j ) (SYM) or f32( dinv64_i * val[e] ) (RW), i.e. the float64
  * products scipy forms before sparse_mx_to_torch_sparse_tensor casts them (util_funcs.py:402). */
@@ -103,7 +111,9 @@ int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
  * D^-1/2 / D^-1 from the row lengths on the fly -- A_hat is never materialised.
  *   dinv     : float32[n] from wdgh_degree_scale (required iff norm != NONE)
  *   plan_i64 / plan_host : from wdgh_plan_build (required)
- *   partial  : float32[n_chunks * roundup(d,4)] scratch for split rows (may be NULL if n_chunks == 0)
+ *   partial  : float32[max(n_chunks, 2 * n_units) * roundup(d,4)] scratch: partial sums of split rows
+ *              (row kernels) or of rows crossing stream-unit boundaries (nnz-balanced kernel, used when
+ *              d % 4 == 0 and d >= 128); n_chunks = plan_host[1], n_units = plan_host[5]
  *   row_offset : 0 for a whole graph.  For a 1-D row shard (multi-GPU) the CSR holds rows
  *              [row_offset, row_offset + n) of the global matrix: `col`, `x` and `dinv` use global
  *              node ids, `y` is local ([n][d]).
@@ -111,6 +121,7 @@ int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
 int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                   const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                   int norm, int add_self_loop, const float *dinv,
+                  const uint8_t *deg_code /* nullable: from wdgh_degree_scale, global ids like dinv */,
                   const int64_t *plan_i64, const int64_t *plan_host, float *partial,
                   int64_t row_offset, void *stream);
 
@@ -144,6 +155,9 @@ int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, 
                           const int64_t *plan_i64, const int64_t *plan_host,
                           int64_t *counters, double *node_sum,
                           int32_t *deg_nsl, int32_t *match_nsl,
+                          uint8_t *labels_u8_scratch /* nullable: uint8[n_labels]; when given and C <= 254 the
+                                                        neighbour-label gathers use a 1-byte copy (L2-resident) */,
+                          int64_t n_labels /* length of `labels` (= n for a whole graph, n_global for a shard) */,
                           int64_t row_offset /* as in wdgh_spmm_csr: labels are global, deg/match local */,
                           void *stream);
 /* Same statistics from an arbitrary edge list (torch `edge_index` int64[2][E]: unsorted, repeats

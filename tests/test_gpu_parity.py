@@ -356,10 +356,10 @@ def test_gram_vs_torch_fp64(W):
 def test_abi_rejects_bad_arguments(W):
     import ctypes as C
     lib = W._lib.lib
-    assert lib.wdgh_spmm_csr(None, None, None, 4, None, 4, 4, None, 4, 0, 0, None, None, None, None, 0, None) == -1
+    assert lib.wdgh_spmm_csr(None, None, None, 4, None, 4, 4, None, 4, 0, 0, None, None, None, None, None, 0, None) == -1
     assert b"null pointer" in lib.wdgh_last_error()
-    host = (C.c_int64 * 4)()
-    assert lib.wdgh_plan_build(None, 4, 512, None, 4, host, None) == -1
+    host = (C.c_int64 * 8)()
+    assert lib.wdgh_plan_build(None, 4, 0, 512, None, 4, host, None) == -1
     with pytest.raises(ValueError):
         g = W.CSRGraph.from_csr(torch.zeros(5, dtype=torch.int64), torch.zeros(0, dtype=torch.int32), None, 4)
         W.spmm(g, torch.zeros(3, 2))

@@ -97,16 +97,22 @@ constexpr int kPlanNHeavy = 0;      // number of split rows
 constexpr int kPlanNChunks = 1;     // number of chunks over all split rows
 constexpr int kPlanThreshold = 2;   // heavy threshold (entries)
 constexpr int kPlanCapacity = 3;    // capacity (chunks) of the three arrays below
+constexpr int kPlanUnit = 4;        // entries per stream unit (WDGH_UNIT)
+constexpr int kPlanNUnits = 5;      // number of stream units = ceil(nnz / unit)
 // arrays after the header, each `capacity` long:
 //   heavy_row[k]      row id of split row k
 //   heavy_chunk0[k]   first chunk id of split row k
 //   chunk_owner[c]    split-row index k that owns chunk c
+// followed by unit_row[u] (n_units long): the row that contains stored entry u * unit
 __host__ __device__ inline const int64_t *plan_heavy_row(const int64_t *p) { return p + WDGH_PLAN_HEADER; }
 __host__ __device__ inline const int64_t *plan_heavy_chunk0(const int64_t *p, int64_t cap) {
   return p + WDGH_PLAN_HEADER + cap;
 }
 __host__ __device__ inline const int64_t *plan_chunk_owner(const int64_t *p, int64_t cap) {
   return p + WDGH_PLAN_HEADER + 2 * cap;
+}
+__host__ __device__ inline const int64_t *plan_unit_row(const int64_t *p, int64_t cap) {
+  return p + WDGH_PLAN_HEADER + 3 * cap;
 }
 
 }  // namespace wdgh

@@ -8,7 +8,7 @@ namespace wdgh {
 // dinv[i] = f32( (rowsum_i + self)^p ), computed in float64 like scipy does, inf -> 0.
 __global__ void degree_scale_kernel(const int64_t *__restrict__ rowptr, const float *__restrict__ val, int64_t n,
                                     int norm, int self_loop, float *__restrict__ dinv,
-                                    double *__restrict__ dinv64) {
+                                    double *__restrict__ dinv64, uint8_t *__restrict__ deg_code) {
   if (val == nullptr) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -22,6 +22,10 @@ __global__ void degree_scale_kernel(const int64_t *__restrict__ rowptr, const fl
       }
       if (dinv) dinv[i] = (float)r;
       if (dinv64) dinv64[i] = r;
+      if (deg_code) {  // stored entries per row, saturated: 255 = "look the scale up in dinv"
+        const int64_t len = rowptr[i + 1] - rowptr[i];
+        deg_code[i] = (uint8_t)(len < 255 ? len : 255);
+      }
     }
     return;
   }
@@ -108,13 +112,15 @@ __global__ void dense_apply_scale_kernel(const float *__restrict__ x, int64_t n,
 using namespace wdgh;
 
 extern "C" int wdgh_degree_scale(const int64_t *rowptr, const float *val, int64_t n, int norm, int add_self_loop,
-                                 float *dinv, double *dinv64, void *stream) {
+                                 float *dinv, double *dinv64, uint8_t *deg_code, void *stream) {
   WDGH_REQUIRE(rowptr && (dinv || dinv64) && n >= 0, "wdgh_degree_scale: bad arguments");
   WDGH_REQUIRE(norm == WDGH_NORM_RW || norm == WDGH_NORM_SYM, "wdgh_degree_scale: norm must be RW or SYM");
+  WDGH_REQUIRE(deg_code == nullptr || val == nullptr, "wdgh_degree_scale: degree codes need a binary adjacency");
   if (n == 0) return 0;
   const int64_t ctas = val ? ceil_div(n, 8) : ceil_div(n, 256);
   degree_scale_kernel<<<persistent_grid(ctas, 8), 256, 0, as_stream(stream)>>>(rowptr, val, n, norm,
-                                                                             add_self_loop ? 1 : 0, dinv, dinv64);
+                                                                             add_self_loop ? 1 : 0, dinv, dinv64,
+                                                                             deg_code);
   WDGH_LAUNCHED("degree_scale_kernel");
   return 0;
 }

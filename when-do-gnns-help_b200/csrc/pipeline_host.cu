@@ -5,8 +5,8 @@
 #include "common.cuh"
 
 extern "C" int wdgh_spmm_csr(const int64_t *, const int32_t *, const float *, int64_t, const float *, int64_t,
-                             int64_t, float *, int64_t, int, int, const float *, const int64_t *, const int64_t *,
-                             float *, int64_t, void *);
+                             int64_t, float *, int64_t, int, int, const float *, const uint8_t *, const int64_t *,
+                             const int64_t *, float *, int64_t, void *);
 
 namespace wdgh {
 
@@ -17,12 +17,13 @@ struct HostPipelineCache {
   int32_t *col = nullptr;
   float *x = nullptr, *y = nullptr, *dinv = nullptr, *partial = nullptr;
   int32_t *labels = nullptr, *deg = nullptr, *match = nullptr;
+  uint8_t *labels8 = nullptr, *deg_code = nullptr;
   int64_t *plan = nullptr, *counters = nullptr;
   double *node_sum = nullptr;
   cudaStream_t st = nullptr;
   void release() {
     cudaFree(rowptr); cudaFree(col); cudaFree(x); cudaFree(y); cudaFree(dinv); cudaFree(partial);
-    cudaFree(labels); cudaFree(deg); cudaFree(match); cudaFree(plan); cudaFree(counters); cudaFree(node_sum);
+    cudaFree(labels); cudaFree(labels8); cudaFree(deg_code); cudaFree(deg); cudaFree(match); cudaFree(plan); cudaFree(counters); cudaFree(node_sum);
     if (st) cudaStreamDestroy(st);
     *this = HostPipelineCache();
   }
@@ -58,9 +59,11 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMalloc(&c.y, n * d * sizeof(float)));
     WDGH_CUDA(cudaMalloc(&c.dinv, n * sizeof(float)));
     WDGH_CUDA(cudaMalloc(&c.labels, n * sizeof(int32_t)));
+    WDGH_CUDA(cudaMalloc(&c.labels8, n));
+    WDGH_CUDA(cudaMalloc(&c.deg_code, n));
     WDGH_CUDA(cudaMalloc(&c.deg, n * sizeof(int32_t)));
     WDGH_CUDA(cudaMalloc(&c.match, n * sizeof(int32_t)));
-    WDGH_CUDA(cudaMalloc(&c.plan, (WDGH_PLAN_HEADER + 3 * cap) * sizeof(int64_t)));
+    WDGH_CUDA(cudaMalloc(&c.plan, WDGH_PLAN_WORDS(cap, nnz) * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.counters, n_counters * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.node_sum, sizeof(double)));
     c.n = n; c.nnz = nnz; c.d = d; c.C = C; c.cap = cap;
@@ -70,25 +73,27 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   if (nnz) WDGH_CUDA(cudaMemcpyAsync(c.col, col_host, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   WDGH_CUDA(cudaMemcpyAsync(c.labels, labels_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   WDGH_CUDA(cudaMemcpyAsync(c.x, x_host, n * d * sizeof(float), cudaMemcpyHostToDevice, st));
-  int64_t plan_host[4];
-  int rc = wdgh_plan_build(c.rowptr, n, kHostPipelineThreshold, c.plan, cap, plan_host, st);
+  int64_t plan_host[8];
+  int rc = wdgh_plan_build(c.rowptr, n, nnz, kHostPipelineThreshold, c.plan, cap, plan_host, st);
   if (rc) return rc;
   const int64_t ldp = (d + 3) & ~int64_t(3);
-  if (plan_host[1] * ldp > c.partial_elems) {
+  const int64_t n_part = plan_host[1] > 2 * plan_host[5] ? plan_host[1] : 2 * plan_host[5];
+  if (n_part * ldp > c.partial_elems) {
     cudaFree(c.partial);
     c.partial = nullptr;
-    c.partial_elems = plan_host[1] * ldp;
+    c.partial_elems = n_part * ldp;
     WDGH_CUDA(cudaMalloc(&c.partial, c.partial_elems * sizeof(float)));
   }
   if (norm != WDGH_NORM_NONE) {
-    rc = wdgh_degree_scale(c.rowptr, nullptr, n, norm, add_self_loop, c.dinv, nullptr, st);
+    rc = wdgh_degree_scale(c.rowptr, nullptr, n, norm, add_self_loop, c.dinv, nullptr, c.deg_code, st);
     if (rc) return rc;
   }
   rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x, d, d, c.y, d, norm, add_self_loop,
-                     norm != WDGH_NORM_NONE ? c.dinv : nullptr, c.plan, plan_host, c.partial, 0, st);
+                     norm != WDGH_NORM_NONE ? c.dinv : nullptr, norm != WDGH_NORM_NONE ? c.deg_code : nullptr, c.plan,
+                     plan_host, c.partial, 0, st);
   if (rc) return rc;
   rc = wdgh_structure_counts(c.rowptr, c.col, n, nnz, c.labels, C, c.plan, plan_host, c.counters, c.node_sum, c.deg,
-                             c.match, 0, st);
+                             c.match, c.labels8, n, 0, st);
   if (rc) return rc;
   WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,9 @@
 //   * degree-binned load balance: rows longer than the plan's threshold are skipped
 //     here and split into fixed-size chunks, one warp per chunk, summed in a fixed
 //     order by a second small kernel (deterministic, no float atomics).
+#include <limits.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wdgh {
@@ -198,6 +201,341 @@ spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// Persistent, software-pipelined row kernel (d % 4 == 0, d >= 128): one warp per CTA walks rows
+// row, row + W, row + 2W, ...  The dependent chain of the plain row kernel
+//     rowptr -> column ids -> D^-1/2 gather -> feature rows (U at a time) -> store
+// is cut to the feature-row batches: row bounds are fetched two rows ahead, the next row's column
+// ids (and scales) right after the current row's first gather batch has been issued.
+// For a binary adjacency the per-entry D^-1/2 gather (a second DRAM row activation per entry when
+// the float array exceeds L2) is replaced by a 1-byte degree code (n bytes, L2-resident) and a
+// 256-entry table in shared memory that holds bit-identical float values.
+// ---------------------------------------------------------------------------
+template <int NCH, bool HAS_VAL, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                           const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
+                           float *__restrict__ y, int64_t ldy, int norm, int self_loop,
+                           const float *__restrict__ dinv, const uint8_t *__restrict__ deg_code, int64_t threshold,
+                           int64_t row_offset) {
+  constexpr int U = (NCH >= 4) ? 2 : (NCH == 2 ? 4 : 8);
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ float table[256];
+  const int lane = threadIdx.x;
+  const bool sym = (norm == WDGH_NORM_SYM);
+  const bool coded = sym && deg_code != nullptr;
+  if (coded) {
+    for (int c = lane; c < 256; c += 32) {
+      double rs = (double)c + (self_loop ? 1.0 : 0.0);
+      if (rs == 0.0) rs = 1.0;
+      table[c] = (float)(1.0 / sqrt(rs));  // same expression as degree_scale_kernel -> same bits
+    }
+    __syncwarp();
+  }
+  const int cbase = blockIdx.y * (128 * NCH);
+  bool live[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) live[t] = cbase + (t * 32 + lane) * 4 < d;
+  const int64_t W = gridDim.x;
+
+  auto bounds = [&](int64_t r, int64_t &s, int64_t &e) {
+    s = 0;
+    e = 0;
+    if (r < n) {
+      s = __ldg(rowptr + r);
+      e = __ldg(rowptr + r + 1);
+    }
+  };
+  auto load_seg = [&](int64_t pos, int64_t e, int &j, float &w) {
+    j = 0;
+    w = 0.f;
+    const int64_t idx = pos + lane;
+    if (idx < e) {
+      j = __ldg(col + idx);
+      w = HAS_VAL ? __ldg(val + idx) : 1.f;
+      if (coded) {
+        const int c = __ldg(deg_code + j);
+        w *= (c < 255) ? table[c] : __ldg(dinv + j);
+      } else if (sym) {
+        w *= __ldg(dinv + j);
+      }
+    }
+  };
+
+  int64_t row = blockIdx.x, r1 = row + W, r2 = row + 2 * W;
+  int64_t s, e, s1, e1, s2, e2;
+  bounds(row, s, e);
+  bounds(r1, s1, e1);
+  if (e - s > threshold) e = s;      // split rows are handled by the chunk kernels
+  if (e1 - s1 > threshold) e1 = s1;
+  int j, nj = 0;
+  float w, nw = 0.f;
+  load_seg(s, e, j, w);
+
+  while (row < n) {
+    bounds(r2, s2, e2);  // two rows ahead
+    const bool heavy = (__ldg(rowptr + row + 1) - s > threshold);
+    Vec<4> acc[NCH];
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) acc[t].zero();
+    bool next_issued = false;
+    for (int64_t base = s; base < e; base += 32) {
+      if (base != s) load_seg(base, e, j, w);
+      const int cnt = (int)min((int64_t)32, e - base);
+      for (int k = 0; k < cnt; k += U) {
+        Vec<4> v[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool on = k + u < cnt;
+          const int jj = __shfl_sync(kFull, j, on ? k + u : 0);
+          const float *xr = x + (int64_t)jj * ldx + cbase;
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) {
+            if (on && live[t]) v[u][t].load(xr + (t * 32 + lane) * 4);
+            else v[u][t].zero();
+          }
+        }
+        if (!next_issued && base + 32 >= e) {  // last segment of this row: fetch the next row's ids now
+          load_seg(s1, e1, nj, nw);
+          next_issued = true;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float wu = __shfl_sync(kFull, w, (k + u < cnt) ? k + u : 0);
+          if (k + u < cnt) {
+#pragma unroll
+            for (int t = 0; t < NCH; ++t) acc[t].fma(wu, v[u][t]);
+          }
+        }
+      }
+    }
+    if (!next_issued) load_seg(s1, e1, nj, nw);
+    if (!heavy) {
+      const int64_t grow = row + row_offset;
+      const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
+      const float self_w = sym ? si : 1.f;
+#pragma unroll
+      for (int t = 0; t < NCH; ++t) {
+        if (live[t]) {
+          const int c = cbase + (t * 32 + lane) * 4;
+          if (self_loop) {
+            Vec<4> xi;
+            xi.load(x + grow * ldx + c);
+            acc[t].fma(self_w, xi);
+          }
+          acc[t].scale(si);
+          acc[t].store_stream(y + row * ldy + c);
+        }
+      }
+    }
+    row = r1; r1 = r2; r2 += W;
+    s = s1; e = e1;
+    s1 = s2; e1 = e2;
+    if (e1 - s1 > threshold) e1 = s1;
+    j = nj; w = nw;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// nnz-balanced streaming kernel (d % 4 == 0, d >= 128): one warp per UNIT of WDGH_UNIT consecutive
+// stored entries, whatever rows they belong to.  Every warp always has full 32-entry segments and
+// U gathers in flight, a hub row is just many units, and short rows cost no idle lanes -- this is
+// what lets the gather stream approach the measured random-512 B-row ceiling of the part
+// (tools/gather_bw.cu: ~7.0 TB/s).  Rows that cross a unit boundary leave unscaled partial sums in
+// `partial` (head = first row of a unit that started earlier, tail = last row that continues) and
+// are completed in fixed order by spmm_stream_fixup_kernel: deterministic, no float atomics.
+// ---------------------------------------------------------------------------
+template <int NCH, bool HAS_VAL>
+__global__ void __launch_bounds__(32)
+spmm_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                   const float *__restrict__ val, int64_t n, int64_t nnz, const float *__restrict__ x, int d,
+                   int64_t ldx, float *__restrict__ y, int64_t ldy, int norm, int self_loop,
+                   const float *__restrict__ dinv, const int64_t *__restrict__ plan, float *__restrict__ partial,
+                   int64_t ldp, int64_t row_offset) {
+  // Gathered rows are staged in shared memory with cp.async (LDGSTS): bytes in flight are bounded by
+  // the 32 KB ring of this warp, not by registers.  SLOTS rows per stage, 2 stages: stage s+1 is in
+  // flight while stage s is consumed.  Every lane reads back exactly the 16-byte pieces it copied
+  // itself, so cp.async.wait_group is the only synchronisation needed.
+  constexpr int SLOTS = 32 / NCH;
+  constexpr int STAGES = 2;
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ float4 ring[STAGES][SLOTS][32 * NCH];
+  const int lane = threadIdx.x;
+  const int64_t unit = blockIdx.x;
+  const int cbase = blockIdx.y * (128 * NCH);
+  bool live[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) live[t] = cbase + (t * 32 + lane) * 4 < d;
+  const int64_t u0 = unit * WDGH_UNIT;
+  const int64_t u1 = min(u0 + (int64_t)WDGH_UNIT, nnz);
+  const int64_t r0 = (unit == 0) ? 0 : plan_unit_row(plan, plan[kPlanCapacity])[unit];
+  const bool first_partial = __ldg(rowptr + r0) < u0;
+  const float *tscale = (norm == WDGH_NORM_SYM) ? dinv : nullptr;
+
+  // All positions below are 32-bit offsets: rows relative to r0, entries relative to u0.
+  // window of row ends: lane l holds (rowptr[r0 + rbase + 1 + l] - u0), clipped
+  const int n_rel = (int)(n - r0);          // rows from r0 to the end of the matrix
+  const int len = (int)(u1 - u0);           // entries in this unit (<= WDGH_UNIT)
+  int cur = 0, rbase = 0;                   // current row / window base, relative to r0
+  auto load_ends = [&](int base) -> int {
+    const int i = base + 1 + lane;
+    if (i > n_rel) return INT_MAX;
+    const int64_t e = __ldg(rowptr + r0 + i) - u0;
+    return e > (int64_t)INT_MAX ? INT_MAX : (int)e;
+  };
+  int ends = load_ends(0);
+  int cur_end = __shfl_sync(kFull, ends, 0);
+  // finalisation data of the current row, fetched when the row becomes current
+  float si = 1.f;
+  Vec<4> xi[NCH];
+  auto fetch_row = [&]() {
+    if (cur < n_rel) {
+      const int64_t gr = r0 + cur + row_offset;
+      if (norm != WDGH_NORM_NONE) si = __ldg(dinv + gr);
+      if (self_loop) {
+#pragma unroll
+        for (int t = 0; t < NCH; ++t)
+          if (live[t]) xi[t].load(x + gr * ldx + cbase + (t * 32 + lane) * 4);
+      }
+    }
+  };
+  fetch_row();
+  Vec<4> acc[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) acc[t].zero();
+
+  auto flush = [&]() {  // the current row ends here
+    if (cur == 0 && first_partial) {
+      float *head = partial + (2 * unit) * ldp + cbase;
+#pragma unroll
+      for (int t = 0; t < NCH; ++t)
+        if (live[t]) acc[t].store(head + (t * 32 + lane) * 4);
+    } else {
+      const float self_w = (norm == WDGH_NORM_SYM) ? si : 1.f;
+      float *yr = y + (r0 + cur) * ldy + cbase;
+#pragma unroll
+      for (int t = 0; t < NCH; ++t) {
+        if (live[t]) {
+          if (self_loop) acc[t].fma(self_w, xi[t]);
+          acc[t].scale(si);
+          acc[t].store_stream(yr + (t * 32 + lane) * 4);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) acc[t].zero();
+    ++cur;
+    if (cur - rbase == 32) {
+      rbase = cur;
+      ends = load_ends(rbase);
+    }
+    cur_end = __shfl_sync(kFull, ends, cur - rbase);
+    fetch_row();
+  };
+
+  // segment = SLOTS consecutive entries; lane l (< SLOTS) holds column id and weight of entry l
+  auto load_seg = [&](int seg, int &j, float &w) {
+    j = 0;
+    w = 0.f;
+    const int p = seg * SLOTS + lane;
+    if (lane < SLOTS && p < len) {
+      const int64_t idx = u0 + p;
+      j = __ldg(col + idx);
+      w = HAS_VAL ? __ldg(val + idx) : 1.f;
+      if (tscale != nullptr) w *= __ldg(tscale + j);
+    }
+  };
+  auto issue_seg = [&](int seg, int j) {  // async copies of the segment's feature rows into its stage
+    const int cnt = min(SLOTS, len - seg * SLOTS);
+    float4(*stage)[32 * NCH] = ring[seg % STAGES];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int jj = __shfl_sync(kFull, j, k);
+      if (k < cnt) {
+        const float *xr = x + (int64_t)jj * ldx + cbase;
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+          if (live[t]) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[k][t * 32 + lane]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xr + (t * 32 + lane) * 4)
+                         : "memory");
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  while (cur < n_rel && cur_end <= 0) flush();  // leading empty rows (only unit 0 can have them)
+
+  const int nseg = (len + SLOTS - 1) / SLOTS;
+  int j0, j1 = 0;
+  float w0, w1 = 0.f;
+  load_seg(0, j0, w0);
+  if (nseg > 1) load_seg(1, j1, w1);
+  issue_seg(0, j0);
+  for (int seg = 0; seg < nseg; ++seg) {
+    int j2 = 0;
+    float w2 = 0.f;
+    if (seg + 2 < nseg) load_seg(seg + 2, j2, w2);  // ids two segments ahead: ready when their copies are issued
+    if (seg + 1 < nseg) issue_seg(seg + 1, j1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");  // keep one group per iteration
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const int cnt = min(SLOTS, len - seg * SLOTS);
+    float4(*stage)[32 * NCH] = ring[seg % STAGES];
+#pragma unroll 8
+    for (int k = 0; k < cnt; ++k) {
+      const float wk = __shfl_sync(kFull, w0, k);
+#pragma unroll
+      for (int t = 0; t < NCH; ++t) {
+        if (live[t]) {
+          Vec<4> v;
+          v.v = stage[k][t * 32 + lane];
+          acc[t].fma(wk, v);
+        }
+      }
+      const int next_pos = seg * SLOTS + k + 1;
+      while (cur < n_rel && next_pos == cur_end) flush();  // also walks over empty rows that follow
+    }
+    j0 = j1; w0 = w1;
+    j1 = j2; w1 = w2;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (cur < n_rel) {  // the last row of the unit continues in the next unit
+    // head: the unit lies inside one row that started earlier; tail otherwise
+    float *dst = partial + (2 * unit + ((cur == 0 && first_partial) ? 0 : 1)) * ldp + cbase;
+#pragma unroll
+    for (int t = 0; t < NCH; ++t)
+      if (live[t]) acc[t].store(dst + (t * 32 + lane) * 4);
+  }
+}
+
+// One warp per unit: if the unit's first row started in an earlier unit and ends here, sum its
+// partials in unit order (tail of the first unit, heads of the units in between, head of this one).
+__global__ void __launch_bounds__(128)
+spmm_stream_fixup_kernel(const int64_t *__restrict__ rowptr, int64_t nnz, const float *__restrict__ x, int d,
+                         int64_t ldx, float *__restrict__ y, int64_t ldy, int norm, int self_loop,
+                         const float *__restrict__ dinv, const int64_t *__restrict__ plan,
+                         const float *__restrict__ partial, int64_t ldp, int64_t row_offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (unit < 1 || unit >= plan[kPlanNUnits]) return;
+  const int64_t u0 = unit * WDGH_UNIT;
+  const int64_t u1 = min(u0 + (int64_t)WDGH_UNIT, nnz);
+  const int64_t r0 = plan_unit_row(plan, plan[kPlanCapacity])[unit];
+  const int64_t s0 = __ldg(rowptr + r0), e0 = __ldg(rowptr + r0 + 1);
+  if (!(s0 < u0 && e0 <= u1)) return;  // the row does not close in this unit
+  const int64_t uf = s0 / WDGH_UNIT;
+  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + r0 + row_offset) : 1.f;
+  const float self_w = (norm == WDGH_NORM_SYM) ? si : 1.f;
+  for (int c = lane; c < d; c += 32) {
+    float acc = partial[(2 * uf + 1) * ldp + c];
+    for (int64_t v = uf + 1; v <= unit; ++v) acc += partial[(2 * v) * ldp + c];
+    if (self_loop) acc = fmaf(self_w, __ldg(x + (r0 + row_offset) * ldx + c), acc);
+    y[r0 * ldy + c] = acc * si;
+  }
+}
+
 struct SpmmArgs {
   const int64_t *rowptr;
   const int32_t *col;
@@ -210,20 +548,34 @@ struct SpmmArgs {
   int64_t ldy;
   int norm, self_loop;
   const float *dinv;
+  const uint8_t *deg_code;
   const int64_t *plan;
-  int64_t threshold, n_heavy, n_chunks, row_offset;
+  int64_t threshold, n_heavy, n_chunks, row_offset, nnz, n_units;
   float *partial;
   int64_t ldp;
   cudaStream_t st;
 };
 
+// CTA size of the row kernel.  Small CTAs keep warp slots busy when row lengths are skewed (a CTA's
+// slots are only recycled when its longest row finishes).  WDGH_SPMM_BLOCK overrides for experiments.
+static int rows_block_threads() {
+  static int cached = 0;
+  if (cached == 0) {
+    int v = 32;  // measured on B200 (1B-entry power-law graph): 256 -> 123.8 ms, 128 -> 114.7, 64 -> 112.4, 32 -> 111.3
+    if (const char *e = getenv("WDGH_SPMM_BLOCK")) v = atoi(e);
+    cached = (v == 32 || v == 64 || v == 128 || v == 256) ? v : 32;
+  }
+  return cached;
+}
+
 template <int G, int VEC, int NCH, bool HAS_VAL>
 static int launch_rows(const SpmmArgs &a) {
   constexpr int RPW = 32 / G;
-  const int64_t rows_per_cta = (256 / 32) * RPW;
+  const int block = rows_block_threads();
+  const int64_t rows_per_cta = (block / 32) * RPW;
   const int tile = G * VEC * NCH;
   dim3 grid((unsigned)ceil_div(a.n, rows_per_cta), (unsigned)ceil_div(a.d, tile));
-  spmm_rows_kernel<G, VEC, NCH, HAS_VAL><<<grid, 256, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y,
+  spmm_rows_kernel<G, VEC, NCH, HAS_VAL><<<grid, block, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y,
                                                                 a.ldy, a.norm, a.self_loop, a.dinv, a.threshold,
                                                                 a.row_offset);
   WDGH_LAUNCHED("spmm_rows_kernel");
@@ -245,10 +597,87 @@ static int launch_heavy(const SpmmArgs &a) {
   return 0;
 }
 
+template <int NCH, bool HAS_VAL>
+static int launch_stream(const SpmmArgs &a) {
+  // one warp (one unit) per CTA, 32 KB of static shared memory each: up to 7 CTAs = 224 KB in flight per SM
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(spmm_stream_kernel<NCH, HAS_VAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  dim3 grid((unsigned)a.n_units, (unsigned)ceil_div(a.d, 128 * NCH));
+  spmm_stream_kernel<NCH, HAS_VAL><<<grid, 32, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.nnz, a.x, a.d, a.ldx, a.y,
+                                                         a.ldy, a.norm, a.self_loop, a.dinv, a.plan, a.partial, a.ldp,
+                                                         a.row_offset);
+  WDGH_LAUNCHED("spmm_stream_kernel");
+  if (a.n_units > 1) {
+    spmm_stream_fixup_kernel<<<(unsigned)ceil_div(a.n_units, 4), 128, 0, a.st>>>(
+        a.rowptr, a.nnz, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.plan, a.partial, a.ldp,
+        a.row_offset);
+    WDGH_LAUNCHED("spmm_stream_fixup_kernel");
+  }
+  return 0;
+}
+
+// 0 = plain row kernels, 1 = persistent pipelined rows (default), 2 = nnz-balanced cp.async stream
+static int wide_variant() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char *e = getenv("WDGH_SPMM_VARIANT");
+    cached = e ? atoi(e) : 1;
+    if (cached < 0 || cached > 2) cached = 1;
+  }
+  return cached;
+}
+static int pipelined_minb() {
+  static int cached = 0;
+  if (cached == 0) {
+    int v = 32;  // measured (1B-entry graph, d=128): 16 -> 118.1 ms, 24 -> 100.4 ms, 32 -> 95.6 ms
+    if (const char *e = getenv("WDGH_PIPE_MINB")) v = atoi(e);
+    cached = (v == 16 || v == 24 || v == 32) ? v : 32;
+  }
+  return cached;
+}
+
+template <int NCH, bool HAS_VAL>
+static int launch_pipelined(const SpmmArgs &a) {
+  const int minb = (NCH == 1) ? pipelined_minb() : 16;
+  int64_t ctas = (int64_t)sm_count() * minb;
+  if (ctas > a.n) ctas = a.n;
+  dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, 128 * NCH));
+#define WDGH_PIPE_LAUNCH(MINB)                                                                                  \
+  spmm_rows_pipelined_kernel<NCH, HAS_VAL, MINB><<<grid, 32, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, \
+                                                                       a.y, a.ldy, a.norm, a.self_loop, a.dinv,     \
+                                                                       a.deg_code, a.threshold, a.row_offset)
+  switch (minb) {
+    case 32: WDGH_PIPE_LAUNCH(32); break;
+    case 24: WDGH_PIPE_LAUNCH(24); break;
+    default: WDGH_PIPE_LAUNCH(16); break;
+  }
+#undef WDGH_PIPE_LAUNCH
+  WDGH_LAUNCHED("spmm_rows_pipelined_kernel");
+  return 0;
+}
+
 template <bool HAS_VAL>
 static int dispatch(const SpmmArgs &a, bool vec4) {
   int rc;
   const int d = a.d;
+  if (vec4 && d >= 128 && wide_variant() == 1) {
+    if (d <= 128) rc = launch_pipelined<1, HAS_VAL>(a);
+    else if (d <= 256) rc = launch_pipelined<2, HAS_VAL>(a);
+    else rc = launch_pipelined<4, HAS_VAL>(a);
+    if (rc) return rc;
+    if (d <= 128) return launch_heavy<4, 1, HAS_VAL>(a);
+    if (d <= 256) return launch_heavy<4, 2, HAS_VAL>(a);
+    return launch_heavy<4, 4, HAS_VAL>(a);
+  }
+  if (vec4 && d >= 128 && a.n_units > 0 && wide_variant() == 2) {
+    if (d <= 128) return launch_stream<1, HAS_VAL>(a);
+    if (d <= 256) return launch_stream<2, HAS_VAL>(a);
+    return launch_stream<4, HAS_VAL>(a);
+  }
   if (vec4) {
     if (d <= 4) rc = launch_rows<1, 4, 1, HAS_VAL>(a);
     else if (d <= 8) rc = launch_rows<2, 4, 1, HAS_VAL>(a);
@@ -283,8 +712,9 @@ using namespace wdgh;
 
 extern "C" int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                              const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy, int norm,
-                             int add_self_loop, const float *dinv, const int64_t *plan_i64,
-                             const int64_t *plan_host, float *partial, int64_t row_offset, void *stream) {
+                             int add_self_loop, const float *dinv, const uint8_t *deg_code,
+                             const int64_t *plan_i64, const int64_t *plan_host, float *partial, int64_t row_offset,
+                             void *stream) {
   WDGH_REQUIRE(rowptr && x && y && plan_i64 && plan_host, "wdgh_spmm_csr: null pointer");  // col may be NULL iff nnz == 0
   WDGH_REQUIRE(n >= 0 && d > 0 && d <= (1 << 24) && ldx >= d && ldy >= d, "wdgh_spmm_csr: bad shape");
   WDGH_REQUIRE(norm == WDGH_NORM_NONE || norm == WDGH_NORM_RW || norm == WDGH_NORM_SYM, "wdgh_spmm_csr: bad norm");
@@ -294,8 +724,10 @@ extern "C" int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const fl
   if (n == 0) return 0;
   SpmmArgs a;
   a.rowptr = rowptr; a.col = col; a.val = val; a.n = n; a.x = x; a.d = (int)d; a.ldx = ldx; a.y = y; a.ldy = ldy;
-  a.norm = norm; a.self_loop = add_self_loop ? 1 : 0; a.dinv = dinv; a.plan = plan_i64;
+  a.norm = norm; a.self_loop = add_self_loop ? 1 : 0; a.dinv = dinv; a.deg_code = (val == nullptr) ? deg_code : nullptr; a.plan = plan_i64;
   a.n_heavy = plan_host[0]; a.n_chunks = plan_host[1]; a.threshold = plan_host[2];
+  a.n_units = plan_host[5];
+  a.nnz = plan_host[6];
   a.partial = partial; a.ldp = (d + 3) & ~int64_t(3);
   a.row_offset = row_offset;
   a.st = as_stream(stream);

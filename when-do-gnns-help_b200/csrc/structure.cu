@@ -57,12 +57,25 @@ __device__ __forceinline__ void flush(EdgeAcc &a, unsigned long long *counters) 
   }
 }
 
-// G lanes per row, persistent grid.  Split (heavy) rows get deg/match = 0 here and are
-// completed by structure_chunks_kernel.
-template <int G>
+// label fetch: int32 labels as given, or the uint8 copy (0xFF = unlabelled) that keeps the gathered
+// array L2-resident for graphs up to ~100M nodes
+template <typename L>
+__device__ __forceinline__ int load_label(const L *p, int64_t i);
+template <>
+__device__ __forceinline__ int load_label<int32_t>(const int32_t *p, int64_t i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ int load_label<uint8_t>(const uint8_t *p, int64_t i) {
+  const int v = __ldg(p + i);
+  return v == 255 ? -1 : v;
+}
+
+// G lanes per row, 4 entries per lane and iteration (all column ids, then all label gathers, are
+// issued before the first fold), next row's bounds prefetched; persistent grid.  Split (heavy) rows
+// get deg/match = 0 here and are completed by structure_chunks_kernel.
+template <int G, typename L>
 __global__ void __launch_bounds__(256)
 structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
-                      const int32_t *__restrict__ labels, int C, int64_t threshold,
+                      const L *__restrict__ labels, int C, int64_t threshold,
                       unsigned long long *__restrict__ counters, int32_t *__restrict__ deg_nsl,
                       int32_t *__restrict__ match_nsl, int64_t row_offset) {
   extern __shared__ unsigned s_hist[];
@@ -73,33 +86,43 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
     __syncthreads();
   }
   constexpr int RPW = 32 / G;
+  constexpr int EPL = 4;  // entries per lane per iteration
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, grp = lane / G;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   EdgeAcc acc;
-  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * RPW < n; w += nwarps) {
-    const int64_t row = w * RPW + grp;
-    int64_t s = 0, e = 0;
-    int li = -1;
-    bool mine = false;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  auto fetch = [&](int64_t ww, int64_t &s, int64_t &e, int &li) {
+    const int64_t row = ww * RPW + grp;
+    s = 0; e = 0; li = -1;
     if (row < n) {
       s = __ldg(rowptr + row);
       e = __ldg(rowptr + row + 1);
-      mine = (e - s) <= threshold;
-      if (!mine) e = s;
-      li = __ldg(labels + row + row_offset);
+      if (e - s > threshold) e = s;
+      li = load_label<L>(labels, row + row_offset);
     }
-    const int iters = warp_max((int)((e - s + G - 1) / G));
+  };
+  int64_t s, e, ns, ne;
+  int li, nli;
+  if (w * RPW < n) fetch(w, s, e, li);
+  for (; w * RPW < n; w += nwarps) {
+    const int64_t row = w * RPW + grp;
+    if ((w + nwarps) * RPW < n) fetch(w + nwarps, ns, ne, nli);
+    const int iters = warp_max((int)((e - s + G * EPL - 1) / (G * EPL)));
     int m_nsl = 0, d_nsl = 0;
     for (int it = 0; it < iters; ++it) {
-      const int64_t idx = s + (int64_t)it * G + gl;
-      int key = -1;
-      if (idx < e) {
-        const int j = __ldg(col + idx);
-        const int lj = __ldg(labels + j);
-        visit(row + row_offset, li, j, lj, C, acc, m_nsl, d_nsl, key);
+      const int64_t base = s + (int64_t)it * (G * EPL) + gl;
+      int j[EPL], lj[EPL];
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) j[k] = (base + k * G < e) ? __ldg(col + base + k * G) : -1;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) lj[k] = (j[k] >= 0) ? load_label<L>(labels, j[k]) : -1;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        int key = -1;
+        if (j[k] >= 0) visit(row + row_offset, li, j[k], lj[k], C, acc, m_nsl, d_nsl, key);
+        fold_keys(key, s_hist, g_hist, use_smem);
       }
-      fold_keys(key, s_hist, g_hist, use_smem);
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -110,6 +133,7 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
       deg_nsl[row] = d_nsl;
       match_nsl[row] = m_nsl;
     }
+    s = ns; e = ne; li = nli;
   }
   flush(acc, counters);
   if (use_smem) {
@@ -121,10 +145,20 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
   }
 }
 
+// int32 labels -> uint8 (0xFF = negative / unlabelled); requires C <= 254
+__global__ void labels_to_u8_kernel(const int32_t *__restrict__ in, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int v = in[i];
+    out[i] = (v < 0 || v > 254) ? (uint8_t)255 : (uint8_t)v;
+  }
+}
+
 // One warp per chunk of a split row.
+template <typename L>
 __global__ void __launch_bounds__(256)
 structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                        const int32_t *__restrict__ labels, int C, const int64_t *__restrict__ plan,
+                        const L *__restrict__ labels, int C, const int64_t *__restrict__ plan,
                         int64_t n_chunks, unsigned long long *__restrict__ counters,
                         int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl, int64_t row_offset) {
   extern __shared__ unsigned s_hist[];
@@ -144,14 +178,14 @@ structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
     const int64_t part = chunk - plan_heavy_chunk0(plan, cap)[k];
     const int64_t s = __ldg(rowptr + row) + part * T;
     const int64_t e = min(s + T, __ldg(rowptr + row + 1));
-    const int li = __ldg(labels + row + row_offset);
+    const int li = load_label<L>(labels, row + row_offset);
     int m_nsl = 0, d_nsl = 0;
     for (int64_t base = s; base < e; base += 32) {  // warp-uniform trip count
       const int64_t idx = base + lane;
       int key = -1;
       if (idx < e) {
         const int j = __ldg(col + idx);
-        const int lj = __ldg(labels + j);
+        const int lj = load_label<L>(labels, j);
         visit(row + row_offset, li, j, lj, C, acc, m_nsl, d_nsl, key);
       }
       fold_keys(key, s_hist, g_hist, use_smem);
@@ -284,14 +318,37 @@ label_rows_equal_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
   if (lane == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
 }
 
-template <int G>
-static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels, int C,
+template <int G, typename L>
+static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const L *labels, int C,
                        int64_t threshold, unsigned long long *counters, int32_t *deg, int32_t *match,
                        size_t smem, cudaStream_t st, int64_t row_offset) {
   const int64_t ctas = ceil_div(n, (int64_t)8 * (32 / G));
-  structure_rows_kernel<G><<<persistent_grid(ctas, 8), 256, smem, st>>>(rowptr, col, n, labels, C, threshold, counters,
-                                                                       deg, match, row_offset);
+  structure_rows_kernel<G, L><<<persistent_grid(ctas, 8), 256, smem, st>>>(rowptr, col, n, labels, C, threshold,
+                                                                          counters, deg, match, row_offset);
   WDGH_LAUNCHED("structure_rows_kernel");
+  return 0;
+}
+
+// rows + chunks passes for one label representation
+template <typename L>
+static int launch_edge_passes(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz, const L *labels, int C,
+                              const int64_t *plan_i64, const int64_t *plan_host, unsigned long long *cnt,
+                              int32_t *deg_nsl, int32_t *match_nsl, size_t hist_smem, cudaStream_t st,
+                              int64_t row_offset) {
+  const int64_t threshold = plan_host[2], n_chunks = plan_host[1];
+  const double avg = (double)nnz / (double)n;
+  int rc;
+  // 4 entries per lane and iteration: pick G so that one iteration covers a typical row
+  if (avg <= 16.0) rc = launch_rows<4, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else if (avg <= 48.0) rc = launch_rows<8, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else if (avg <= 96.0) rc = launch_rows<16, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else rc = launch_rows<32, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  if (rc) return rc;
+  if (n_chunks > 0) {
+    structure_chunks_kernel<L><<<persistent_grid(ceil_div(n_chunks, 8), 8), 256, hist_smem, st>>>(
+        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl, row_offset);
+    WDGH_LAUNCHED("structure_chunks_kernel");
+  }
   return 0;
 }
 
@@ -302,11 +359,13 @@ using namespace wdgh;
 extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                                      const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
                                      const int64_t *plan_host, int64_t *counters, double *node_sum,
-                                     int32_t *deg_nsl, int32_t *match_nsl, int64_t row_offset, void *stream) {
+                                     int32_t *deg_nsl, int32_t *match_nsl, uint8_t *labels_u8_scratch,
+                                     int64_t n_labels, int64_t row_offset, void *stream) {
   WDGH_REQUIRE(rowptr && labels && plan_i64 && plan_host && counters && node_sum && deg_nsl && match_nsl,
                "wdgh_structure_counts: null pointer");
   WDGH_REQUIRE(n >= 0 && nnz >= 0 && (col || nnz == 0), "wdgh_structure_counts: bad shape");
   WDGH_REQUIRE(num_classes >= 1 && num_classes <= 46340, "wdgh_structure_counts: num_classes out of range");
+  WDGH_REQUIRE(labels_u8_scratch == nullptr || n_labels >= n + row_offset, "wdgh_structure_counts: n_labels too small");
   cudaStream_t st = as_stream(stream);
   const int C = num_classes;
   const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
@@ -315,19 +374,17 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   if (n == 0) return 0;
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
   const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
-  const int64_t threshold = plan_host[2], n_chunks = plan_host[1];
-  const double avg = (double)nnz / (double)n;
   int rc;
-  if (avg <= 6.0) rc = launch_rows<4>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else if (avg <= 12.0) rc = launch_rows<8>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else if (avg <= 24.0) rc = launch_rows<16>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else rc = launch_rows<32>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  if (rc) return rc;
-  if (n_chunks > 0) {
-    structure_chunks_kernel<<<persistent_grid(ceil_div(n_chunks, 8), 8), 256, hist_smem, st>>>(
-        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl, row_offset);
-    WDGH_LAUNCHED("structure_chunks_kernel");
+  if (labels_u8_scratch != nullptr && C <= 254) {
+    labels_to_u8_kernel<<<persistent_grid(ceil_div(n_labels, 256), 8), 256, 0, st>>>(labels, n_labels, labels_u8_scratch);
+    WDGH_LAUNCHED("labels_to_u8_kernel");
+    rc = launch_edge_passes<uint8_t>(rowptr, col, n, nnz, labels_u8_scratch, C, plan_i64, plan_host, cnt, deg_nsl,
+                                     match_nsl, hist_smem, st, row_offset);
+  } else {
+    rc = launch_edge_passes<int32_t>(rowptr, col, n, nnz, labels, C, plan_i64, plan_host, cnt, deg_nsl, match_nsl,
+                                     hist_smem, st, row_offset);
   }
+  if (rc) return rc;
   const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
   structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
                                                                                      match_nsl, cnt, node_sum, row_offset);

@@ -52,6 +52,7 @@ class CSRGraph:
         self._rows = None
         self._dinv = {}
         self._counts = {}
+        self._partial = {}
 
     # ---- constructors ----------------------------------------------------
     @classmethod
@@ -101,10 +102,11 @@ class CSRGraph:
         """(device plan tensor, host int64[4] ctypes array) -- built once per graph."""
         if self._plan is None:
             cap = 2 * self.nnz // self.threshold + 2
-            plan = torch.empty(_lib.PLAN_HEADER + 3 * cap, dtype=torch.int64, device=self.device)
-            host = (C.c_int64 * 4)()
-            check(lib.wdgh_plan_build(ptr(self.rowptr), self.n, self.threshold, ptr(plan), cap, host, stream_ptr()),
-                  "wdgh_plan_build")
+            words = _lib.PLAN_HEADER + 3 * cap + (self.nnz + _lib.UNIT - 1) // _lib.UNIT
+            plan = torch.empty(words, dtype=torch.int64, device=self.device)
+            host = (C.c_int64 * 8)()
+            check(lib.wdgh_plan_build(ptr(self.rowptr), self.n, self.nnz, self.threshold, ptr(plan), cap, host,
+                                      stream_ptr()), "wdgh_plan_build")
             self._plan = (plan, host)
         return self._plan
 
@@ -115,6 +117,10 @@ class CSRGraph:
     @property
     def n_heavy(self):
         return int(self.plan[1][0])
+
+    @property
+    def n_units(self):
+        return int(self.plan[1][5])
 
     def rows(self):
         """int64 row id of every stored entry (COO view)."""
@@ -130,13 +136,15 @@ class CSRGraph:
         return torch.stack([self.rows(), self.col.to(torch.int64)])
 
     def degree_scale(self, norm, self_loop, want64=False):
+        """(dinv float32[n], dinv64 or None, deg_code uint8[n] or None) -- cached per (norm, self_loop)."""
         key = (norm, bool(self_loop), want64)
         if key not in self._dinv:
             dinv = torch.empty(self.n, dtype=torch.float32, device=self.device)
             d64 = torch.empty(self.n, dtype=torch.float64, device=self.device) if want64 else None
+            code = torch.empty(self.n, dtype=torch.uint8, device=self.device) if self.val is None else None
             check(lib.wdgh_degree_scale(ptr(self.rowptr), ptr(self.val), self.n, norm, int(bool(self_loop)),
-                                        ptr(dinv), ptr(d64), stream_ptr()), "wdgh_degree_scale")
-            self._dinv[key] = (dinv, d64)
+                                        ptr(dinv), ptr(d64), ptr(code), stream_ptr()), "wdgh_degree_scale")
+            self._dinv[key] = (dinv, d64, code)
         return self._dinv[key]
 
     def with_self_loops(self):
@@ -154,7 +162,7 @@ class CSRGraph:
 
     def normalized(self, norm):
         """Materialised D^-1/2 A D^-1/2 (SYM) or D^-1 A (RW) of THIS matrix (no self-loop added)."""
-        _, d64 = self.degree_scale(norm, False, want64=True)
+        d64 = self.degree_scale(norm, False, want64=True)[1]
         out = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
         check(lib.wdgh_scale_values(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n, norm, ptr(d64), ptr(out),
                                     stream_ptr()), "wdgh_scale_values")
@@ -170,7 +178,7 @@ class CSRGraph:
 # ---------------------------------------------------------------------------
 # A_hat X aggregation
 # ---------------------------------------------------------------------------
-def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=None):
+def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=None, deg_code=None):
     """y = norm(A [+I]) x in float32 on the GPU (hm.py:192,199,234; util_funcs.py:383-390,418-426).
 
     For a row shard `x` (and `dinv`, the all-gathered degree scale) are global, the result is local."""
@@ -181,14 +189,18 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
     y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=g.device)
     plan, plan_host = g.plan
     ldp = (d + 3) & ~3
-    partial = torch.empty(g.n_chunks * ldp, dtype=torch.float32, device=g.device) if g.n_chunks else None
+    n_part = max(g.n_chunks, 2 * g.n_units) * ldp  # scratch for rows split across chunks / stream units
+    partial = g._partial.get(n_part)
+    if partial is None and n_part:
+        partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
+        g._partial = {n_part: partial}
     if norm != NORM_NONE and dinv is None:
         if g.n_global != g.n:
             raise ValueError("a row shard needs the all-gathered degree scale (dinv=...)")
-        dinv = g.degree_scale(norm, add_self_loop)[0]
+        dinv, _, deg_code = g.degree_scale(norm, add_self_loop)
     check(lib.wdgh_spmm_csr(ptr(g.rowptr), ptr(g.col), ptr(g.val), g.n, ptr(x), d, x.stride(0), ptr(y), y.stride(0),
-                            norm, int(bool(add_self_loop)), ptr(dinv), ptr(plan), plan_host, ptr(partial),
-                            g.row_offset, stream_ptr()), "wdgh_spmm_csr")
+                            norm, int(bool(add_self_loop)), ptr(dinv), ptr(deg_code), ptr(plan), plan_host,
+                            ptr(partial), g.row_offset, stream_ptr()), "wdgh_spmm_csr")
     return y
 
 
@@ -247,21 +259,25 @@ def structure_counts_raw(g: CSRGraph, labels32, num_classes, scratch=None):
     `labels32` is indexed by global node id (length n_global for a row shard)."""
     c = int(num_classes)
     dev = g.device
+    n_labels = int(labels32.shape[0])
+    if n_labels < g.row_offset + g.n:
+        raise ValueError("labels must cover every (global) node id of the shard")
     if scratch is None:
         scratch = (torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev),
                    torch.empty(1, dtype=torch.float64, device=dev),
                    torch.empty(g.n, dtype=torch.int32, device=dev),
-                   torch.empty(g.n, dtype=torch.int32, device=dev))
-    counters, node_sum, deg, match = scratch
+                   torch.empty(g.n, dtype=torch.int32, device=dev),
+                   torch.empty(n_labels, dtype=torch.uint8, device=dev))
+    counters, node_sum, deg, match, lab8 = scratch
     plan, plan_host = g.plan
     check(lib.wdgh_structure_counts(ptr(g.rowptr), ptr(g.col), g.n, g.nnz, ptr(labels32), c, ptr(plan), plan_host,
-                                    ptr(counters), ptr(node_sum), ptr(deg), ptr(match), g.row_offset, stream_ptr()),
-          "wdgh_structure_counts")
-    return counters, node_sum, deg, match
+                                    ptr(counters), ptr(node_sum), ptr(deg), ptr(match), ptr(lab8), n_labels,
+                                    g.row_offset, stream_ptr()), "wdgh_structure_counts")
+    return counters, node_sum, deg, match, lab8
 
 
 def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
-    counters, node_sum, deg, match = structure_counts_raw(g, labels32, num_classes)
+    counters, node_sum, deg, match, _ = structure_counts_raw(g, labels32, num_classes)
     return _unpack_counts(g.n, g.nnz, int(num_classes), counters, node_sum, deg, match)
 
 

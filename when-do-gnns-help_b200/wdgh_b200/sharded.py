@@ -80,7 +80,7 @@ class ShardedStats:
         self.labels_local = _pad_rows(labels_local, part.block)
 
     # -- local compute, overridden -------------------------------------------------------------
-    def local_degree_scale(self, norm, add_self_loop):  # -> float32 [rows_r]
+    def local_degree_scale(self, norm, add_self_loop):  # -> float32 [rows_r] (+ optional uint8 degree codes)
         raise NotImplementedError
 
     def local_compute(self, x_full, labels_full, dinv_full, norm, add_self_loop):
@@ -92,9 +92,13 @@ class ShardedStats:
         x_full = _all_gather_rows(self.x_local, self.group)
         labels_full = _all_gather_rows(self.labels_local, self.group)
         dinv_full = None
+        self.code_full = None
         if norm != _lib.NORM_NONE:
-            dinv = _pad_rows(self.local_degree_scale(norm, add_self_loop), self.part.block)
-            dinv_full = _all_gather_rows(dinv, self.group)
+            loc = self.local_degree_scale(norm, add_self_loop)
+            dinv, code = loc if isinstance(loc, tuple) else (loc, None)
+            dinv_full = _all_gather_rows(_pad_rows(dinv, self.part.block), self.group)
+            if code is not None:
+                self.code_full = _all_gather_rows(_pad_rows(code, self.part.block), self.group)
         return x_full, labels_full, dinv_full
 
     def reduce_counters(self, counters, node_sum):
@@ -128,13 +132,13 @@ class CudaShardedStats(ShardedStats):
 
     def local_degree_scale(self, norm, add_self_loop):
         self.g._dinv.clear()  # recomputed every step: it is part of the timed path
-        return self.g.degree_scale(norm, add_self_loop)[0]
+        dinv, _, code = self.g.degree_scale(norm, add_self_loop)
+        return dinv, code
 
     def local_compute(self, x_full, labels_full, dinv_full, norm, add_self_loop):
         G = self._G
         if self._y is None or self._y.shape[1] != x_full.shape[1]:
             self._y = torch.empty((self.g.n, x_full.shape[1]), dtype=torch.float32, device=x_full.device)
-        y = G.spmm(self.g, x_full, norm, add_self_loop, out=self._y, dinv=dinv_full)
-        counters, node_sum, deg, match = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)
-        self._scratch = (counters, node_sum, deg, match)
-        return y, counters, node_sum
+        y = G.spmm(self.g, x_full, norm, add_self_loop, out=self._y, dinv=dinv_full, deg_code=self.code_full)
+        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)
+        return y, self._scratch[0], self._scratch[1]
