@@ -187,10 +187,12 @@ int wdgh_edge_cosine(const int64_t *rowptr, const int32_t *col, const float *val
 
 /* ---- dense contractions: aggregation similarity and the KR Gram ---------- */
 /* g[m][m] = z z^T for z float32[m][d]  ((A X)(A X)^T, hm.py:192,199-200,234-235,246).
- * Runs on tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM) when
- * `use_tensor_cores` != 0, otherwise on a SIMT fp32 tile kernel. */
+ * use_tensor_cores != 0: TMA-fed tcgen05 kernel, 3xTF32 operand split (fp32-level accuracy), fp32
+ *   accumulation in TMEM; needs `workspace` = float32[wdgh_gram_workspace_floats(m, d)], 16-byte aligned.
+ * use_tensor_cores == 0: SIMT fp32 tile kernel (cross-check), workspace may be NULL. */
+int64_t wdgh_gram_workspace_floats(int64_t m, int64_t d);
 int wdgh_gram(const float *z, int64_t m, int64_t d, int64_t ldz,
-              float *g, int64_t ldg, int use_tensor_cores, void *stream);
+              float *g, int64_t ldg, int use_tensor_cores, float *workspace, void *stream);
 /* gather rows: out[k][:] = x[ids[k]][:]  (torch indexing `[sample, :]`, hm.py:199,234,246) */
 int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const int64_t *ids, int64_t m,
                      float *out, int64_t ldo, void *stream);

@@ -1,5 +1,5 @@
-// Dense side of the path: row gathers, the SIMT fp32 Gram kernel (reference for / fallback of
-// the tcgen05 kernel in gram_tc.cu -- both run on the GPU), class-wise column sums and the
+// Dense side of the path: row gathers, the SIMT fp32 Gram kernel (the cross-check of the tcgen05
+// kernel in gram_tc.cu; both run on the GPU, the caller picks one explicitly), class-wise column sums and the
 // aggregation-similarity score (utils/homophily_metrics.py:190-229), the arccos (GNTK) kernel
 // transform (:232-257) and the per-edge feature cosine of generalised edge homophily (:164-187).
 #include <math_constants.h>
@@ -269,7 +269,8 @@ edge_cosine_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
 
 using namespace wdgh;
 
-int wdgh_gram_tc_launch(const float *z, int64_t m, int64_t d, int64_t ldz, float *g, int64_t ldg, cudaStream_t st);
+int wdgh_gram_tc_launch(const float *z, int64_t m, int64_t d, int64_t ldz, float *g, int64_t ldg, float *workspace,
+                        cudaStream_t st);
 
 extern "C" int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const int64_t *ids, int64_t m, float *out,
                                 int64_t ldo, void *stream) {
@@ -281,11 +282,11 @@ extern "C" int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const in
 }
 
 extern "C" int wdgh_gram(const float *z, int64_t m, int64_t d, int64_t ldz, float *g, int64_t ldg,
-                         int use_tensor_cores, void *stream) {
+                         int use_tensor_cores, float *workspace, void *stream) {
   WDGH_REQUIRE(z && g && m >= 0 && d >= 1 && ldz >= d && ldg >= m, "wdgh_gram: bad arguments");
   if (m == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (use_tensor_cores) return wdgh_gram_tc_launch(z, m, d, ldz, g, ldg, st);
+  if (use_tensor_cores) return wdgh_gram_tc_launch(z, m, d, ldz, g, ldg, workspace, st);
   dim3 grid((unsigned)ceil_div(m, 64), (unsigned)ceil_div(m, 64));
   gram_simt_kernel<<<grid, 256, 0, st>>>(z, m, d, ldz, g, ldg);
   WDGH_LAUNCHED("gram_simt_kernel");

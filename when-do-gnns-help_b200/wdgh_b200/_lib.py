@@ -47,7 +47,8 @@ SIGNATURES = {
     "wdgh_structure_counts_coo": [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p],
     "wdgh_edge_label_rows_equal": [_p, _p, _i64, _p, _i64, _i64, _p, _p],
     "wdgh_edge_cosine": [_p, _p, _p, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p],
-    "wdgh_gram": [_p, _i64, _i64, _i64, _p, _i64, _int, _p],
+    "wdgh_gram_workspace_floats": [_i64, _i64],
+    "wdgh_gram": [_p, _i64, _i64, _i64, _p, _i64, _int, _p, _p],
     "wdgh_gather_rows": [_p, _i64, _i64, _p, _i64, _p, _i64, _p],
     "wdgh_class_colsum": [_p, _i64, _i64, _p, _i32, _int, _p, _p],
     "wdgh_las_score": [_p, _p, _p, _i64, _i32, _int, _int, _int, _p, _p, _p],
@@ -55,7 +56,7 @@ SIGNATURES = {
     "wdgh_pipeline_host": [_p, _p, _i64, _i64, _p, _i64, _p, _i32, _int, _int, _p, _p, _p],
     "wdgh_pipeline_host_release": [],
 }
-_RESTYPE = {"wdgh_last_error": C.c_char_p, "wdgh_launch_count": C.c_uint64}
+_RESTYPE = {"wdgh_last_error": C.c_char_p, "wdgh_launch_count": C.c_uint64, "wdgh_gram_workspace_floats": C.c_int64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header / library mismatch

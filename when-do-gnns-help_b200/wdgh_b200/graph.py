@@ -321,7 +321,12 @@ def edge_cosine(g: CSRGraph, x, entry_ids=None):
 # ---------------------------------------------------------------------------
 # dense contractions
 # ---------------------------------------------------------------------------
-USE_TENSOR_CORES = False  # flipped to True once gram_tc.cu is validated on the B200
+USE_TENSOR_CORES = True  # tcgen05 / TMEM Gram (csrc/gram_tc.cu); False selects the SIMT fp32 cross-check kernel
+# The KR metric feeds its Gram to np.linalg.pinv(rcond=1e-15): the matrix is rank-deficient (rank <= d),
+# so rounding noise of the Gram is amplified into the predictions.  The float32-FMA SIMT kernel reproduces
+# the reference's torch.mm noise level (golden p-values match); the 3xTF32 tensor-core result is within
+# 1e-5 of the exact Gram but not noise-compatible, so KR defaults to the SIMT kernel.
+KR_USE_TENSOR_CORES = False
 
 
 def gather_rows(x, ids):
@@ -339,7 +344,10 @@ def gram(z, use_tensor_cores=None):
     m, d = int(z.shape[0]), int(z.shape[1])
     g = torch.empty((m, m), dtype=torch.float32, device=z.device)
     tc = USE_TENSOR_CORES if use_tensor_cores is None else use_tensor_cores
-    check(lib.wdgh_gram(ptr(z), m, d, z.stride(0), ptr(g), m, int(bool(tc)), stream_ptr()), "wdgh_gram")
+    ws = None
+    if tc:
+        ws = torch.empty(int(lib.wdgh_gram_workspace_floats(m, d)), dtype=torch.float32, device=z.device)
+    check(lib.wdgh_gram(ptr(z), m, d, z.stride(0), ptr(g), m, int(bool(tc)), ptr(ws), stream_ptr()), "wdgh_gram")
     return g
 
 
