@@ -211,13 +211,14 @@ spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__rest
 // the float array exceeds L2) is replaced by a 1-byte degree code (n bytes, L2-resident) and a
 // 256-entry table in shared memory that holds bit-identical float values.
 // ---------------------------------------------------------------------------
-template <int NCH, bool HAS_VAL, int MINB>
+template <int NCH, bool HAS_VAL, bool FULL, int MINB>
 __global__ void __launch_bounds__(32, MINB)
 spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                            const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
                            float *__restrict__ y, int64_t ldy, int norm, int self_loop,
                            const float *__restrict__ dinv, const uint8_t *__restrict__ deg_code, int64_t threshold,
                            int64_t row_offset) {
+  // FULL: d == 128 * NCH, i.e. no column tail and a single column tile -> no per-load predicates
   constexpr int U = (NCH >= 4) ? 2 : (NCH == 2 ? 4 : 8);
   constexpr unsigned kFull = 0xffffffffu;
   __shared__ float table[256];
@@ -232,11 +233,13 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     }
     __syncwarp();
   }
-  const int cbase = blockIdx.y * (128 * NCH);
+  const int cbase = FULL ? 0 : blockIdx.y * (128 * NCH);
   bool live[NCH];
 #pragma unroll
-  for (int t = 0; t < NCH; ++t) live[t] = cbase + (t * 32 + lane) * 4 < d;
+  for (int t = 0; t < NCH; ++t) live[t] = FULL || (cbase + (t * 32 + lane) * 4 < d);
   const int64_t W = gridDim.x;
+  const int ld32 = (int)ldx;                       // row stride in floats (< 2^31): one IMAD.WIDE per gather
+  const float *xl = x + cbase + lane * 4;          // this lane's column slice of row 0
 
   auto bounds = [&](int64_t r, int64_t &s, int64_t &e) {
     s = 0;
@@ -266,15 +269,16 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
   int64_t s, e, s1, e1, s2, e2;
   bounds(row, s, e);
   bounds(r1, s1, e1);
-  if (e - s > threshold) e = s;      // split rows are handled by the chunk kernels
-  if (e1 - s1 > threshold) e1 = s1;
+  bool heavy = (e - s > threshold);   // split rows are handled by the chunk kernels
+  if (heavy) e = s;
+  bool heavy1 = (e1 - s1 > threshold);
+  if (heavy1) e1 = s1;
   int j, nj = 0;
   float w, nw = 0.f;
   load_seg(s, e, j, w);
 
   while (row < n) {
     bounds(r2, s2, e2);  // two rows ahead
-    const bool heavy = (__ldg(rowptr + row + 1) - s > threshold);
     Vec<4> acc[NCH];
 #pragma unroll
     for (int t = 0; t < NCH; ++t) acc[t].zero();
@@ -282,20 +286,43 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     for (int64_t base = s; base < e; base += 32) {
       if (base != s) load_seg(base, e, j, w);
       const int cnt = (int)min((int64_t)32, e - base);
-      for (int k = 0; k < cnt; k += U) {
+      const bool last_seg = base + 32 >= e;
+      int k = 0;
+      for (; k + U <= cnt; k += U) {  // full batches: U unpredicated gathers in flight
+        Vec<4> v[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, k + u) * ld32;
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) {
+            if (live[t]) v[u][t].load(xr + t * 128);
+            else v[u][t].zero();
+          }
+        }
+        if (!next_issued && last_seg) {  // fetch the next row's ids while this row's gathers are in flight
+          load_seg(s1, e1, nj, nw);
+          next_issued = true;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float wu = __shfl_sync(kFull, w, k + u);
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) acc[t].fma(wu, v[u][t]);
+        }
+      }
+      if (k < cnt) {  // tail batch, predicated
         Vec<4> v[U][NCH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool on = k + u < cnt;
-          const int jj = __shfl_sync(kFull, j, on ? k + u : 0);
-          const float *xr = x + (int64_t)jj * ldx + cbase;
+          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, on ? k + u : 0) * ld32;
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
-            if (on && live[t]) v[u][t].load(xr + (t * 32 + lane) * 4);
+            if (on && live[t]) v[u][t].load(xr + t * 128);
             else v[u][t].zero();
           }
         }
-        if (!next_issued && base + 32 >= e) {  // last segment of this row: fetch the next row's ids now
+        if (!next_issued && last_seg) {
           load_seg(s1, e1, nj, nw);
           next_issued = true;
         }
@@ -329,9 +356,10 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
       }
     }
     row = r1; r1 = r2; r2 += W;
-    s = s1; e = e1;
+    s = s1; e = e1; heavy = heavy1;
     s1 = s2; e1 = e2;
-    if (e1 - s1 > threshold) e1 = s1;
+    heavy1 = (e1 - s1 > threshold);
+    if (heavy1) e1 = s1;
     j = nj; w = nw;
   }
 }
@@ -646,14 +674,19 @@ static int launch_pipelined(const SpmmArgs &a) {
   int64_t ctas = (int64_t)sm_count() * minb;
   if (ctas > a.n) ctas = a.n;
   dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, 128 * NCH));
-#define WDGH_PIPE_LAUNCH(MINB)                                                                                  \
-  spmm_rows_pipelined_kernel<NCH, HAS_VAL, MINB><<<grid, 32, 0, a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, \
-                                                                       a.y, a.ldy, a.norm, a.self_loop, a.dinv,     \
-                                                                       a.deg_code, a.threshold, a.row_offset)
-  switch (minb) {
-    case 32: WDGH_PIPE_LAUNCH(32); break;
-    case 24: WDGH_PIPE_LAUNCH(24); break;
-    default: WDGH_PIPE_LAUNCH(16); break;
+  const bool full = (a.d == 128 * NCH);
+#define WDGH_PIPE_LAUNCH(FULLV, MINB)                                                                              \
+  spmm_rows_pipelined_kernel<NCH, HAS_VAL, FULLV, MINB><<<grid, 32, 0, a.st>>>(                                       \
+      a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
+      a.row_offset)
+  if (full) {
+    switch (minb) {
+      case 32: WDGH_PIPE_LAUNCH(true, 32); break;
+      case 24: WDGH_PIPE_LAUNCH(true, 24); break;
+      default: WDGH_PIPE_LAUNCH(true, 16); break;
+    }
+  } else {
+    WDGH_PIPE_LAUNCH(false, 16);
   }
 #undef WDGH_PIPE_LAUNCH
   WDGH_LAUNCHED("spmm_rows_pipelined_kernel");
