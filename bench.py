@@ -246,8 +246,8 @@ def main():
         def step():
             g._dinv.clear()
             dinv, _, code = g.degree_scale(W.NORM_SYM, True)
-            G.spmm(g, x_local, W.NORM_SYM, True, out=y, dinv=dinv, deg_code=code)
-            scratch[0] = G.structure_counts_raw(g, labels_local, C, scratch[0])
+            _, scratch[0] = G.spmm_structure_fused(g, x_local, labels_local, C, W.NORM_SYM, True, out=y, dinv=dinv,
+                                                   deg_code=code, scratch=scratch[0])
             return scratch[0][0], scratch[0][1]
     else:
         pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C)
@@ -319,7 +319,7 @@ def main():
         traffic = traffic * nnz_local if traffic is not None else None
     except Exception:
         pass
-    roofline = {"kernel": "spmm_rows_kernel<32,4,1>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "spmm_rows_pipelined_kernel<1,0,1,32> (+ chunk kernels for split rows)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": spmm_ms, "algorithmic_bytes": alg_bytes, "share_of_step": spmm_ms / ms}
 

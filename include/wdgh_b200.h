@@ -149,6 +149,7 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
 #define WDGH_SC_N_EMPTY     4
 #define WDGH_SC_NBINS       5
 #define WDGH_SC_N_NODES_NSL 6
+#define WDGH_SC_N_MULTI_NEG 7 /* labels < -1 seen while packing to 1 byte: re-run without labels_u8_scratch */
 #define WDGH_SC_HEADER      8
 int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                           const int32_t *labels, int32_t num_classes,
@@ -160,6 +161,19 @@ int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, 
                           int64_t n_labels /* length of `labels` (= n for a whole graph, n_global for a shard) */,
                           int64_t row_offset /* as in wdgh_spmm_csr: labels are global, deg/match local */,
                           void *stream);
+/* A_hat X aggregation AND the label statistics in one call (binary adjacency): the union of
+ * wdgh_spmm_csr and wdgh_structure_counts, same arguments, same results (Y bit-identical, counters
+ * exact).  single_kernel != 0 (and d % 4 == 0, d >= 128, C <= 64, labels_u8_scratch given) folds the
+ * per-entry label work into the aggregation kernel; single_kernel == 0 runs the two passes back to
+ * back, which is the faster form on the B200 and the default of the host mirror. */
+int wdgh_spmm_structure_fused(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
+                              const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
+                              int norm, int add_self_loop, const float *dinv, const uint8_t *deg_code,
+                              const int32_t *labels, int32_t num_classes,
+                              const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                              int64_t *counters, double *node_sum, int32_t *deg_nsl, int32_t *match_nsl,
+                              uint8_t *labels_u8_scratch, int64_t n_labels, int64_t row_offset,
+                              int single_kernel, void *stream);
 /* Same statistics from an arbitrary edge list (torch `edge_index` int64[2][E]: unsorted, repeats
  * counted with multiplicity), as node_homophily_edge_idx / compact_matrix_edge_idx / our_measure
  * receive it (hm.py:71,81,105).  Row lengths are unknown here, so the per-class degree mass

@@ -344,6 +344,48 @@ def test_properties_large(W):
     assert s2.match_all == s.match_all and abs(s2.node_sum - s.node_sum) < 1e-6 * max(1.0, s.node_sum)
 
 
+@pytest.mark.parametrize("d,c", [(128, 10), (256, 3), (384, 64), (128, 70), (64, 5)])
+def test_fused_pass_equals_separate_passes(W, d, c):
+    """wdgh_spmm_structure_fused == wdgh_spmm_csr + wdgh_structure_counts (Y bit-identical, integers exact)."""
+    n = 30000
+    row, col, _ = powerlaw_graph(n, 12, seed=d + c)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    rng = np.random.default_rng(d)
+    labels = rng.integers(0, c, n).astype(np.int64)
+    labels[:c] = np.arange(c)
+    labels[rng.random(n) < 0.05] = -1
+    x = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), None, n, threshold=256)
+    assert g.n_heavy > 0
+    lab32, mx = W.graph.pack_labels(torch.from_numpy(labels))
+    y_ref = W.spmm(g, x, W.NORM_SYM, True)
+    s_ref = W.graph.structure_counts(g, lab32, c)
+    for single in (True, False):
+        y, (counters, node_sum, deg, match, _) = W.graph.spmm_structure_fused(g, x, lab32, c, W.NORM_SYM, True,
+                                                                              single_kernel=single)
+        s = W.graph._unpack_counts(g.n, g.nnz, c, counters, node_sum, deg, match)
+        assert torch.equal(y, y_ref)
+        assert (s.match_all, s.match_lab, s.n_lab, s.n_self, s.n_empty, s.nbins, s.n_nodes_nsl) == \
+               (s_ref.match_all, s_ref.match_lab, s_ref.n_lab, s_ref.n_self, s_ref.n_empty, s_ref.nbins, s_ref.n_nodes_nsl)
+        assert np.array_equal(s.hist, s_ref.hist) and np.array_equal(s.class_deg, s_ref.class_deg)
+        assert torch.equal(s.deg_nsl, s_ref.deg_nsl) and torch.equal(s.match_nsl, s_ref.match_nsl)
+        assert abs(s.node_sum - s_ref.node_sum) <= 1e-9 * max(1.0, s_ref.node_sum)
+        o = O.structure_counts(row, col, labels, n, num_classes=c)
+        assert np.array_equal(s.hist, o["hist"]) and s.match_all == o["match_all"]
+
+
+def test_distinct_negative_labels_fall_back_to_int32(W):
+    n = 5000
+    row, col, _ = powerlaw_graph(n, 8, seed=1)
+    rng = np.random.default_rng(0)
+    labels = rng.integers(0, 3, n).astype(np.int64)
+    labels[rng.random(n) < 0.2] = -1
+    labels[rng.random(n) < 0.1] = -2      # two different "unlabelled" codes: raw equality must tell them apart
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), None, n)
+    check_counts_exact(W, g, labels, row, col, n)
+
+
 def test_gram_vs_torch_fp64(W):
     gen = torch.Generator(device="cuda").manual_seed(0)
     for m, d in ((1, 1), (63, 7), (64, 16), (500, 1433), (1000, 10), (777, 130)):

@@ -88,12 +88,10 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     rc = wdgh_degree_scale(c.rowptr, nullptr, n, norm, add_self_loop, c.dinv, nullptr, c.deg_code, st);
     if (rc) return rc;
   }
-  rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x, d, d, c.y, d, norm, add_self_loop,
-                     norm != WDGH_NORM_NONE ? c.dinv : nullptr, norm != WDGH_NORM_NONE ? c.deg_code : nullptr, c.plan,
-                     plan_host, c.partial, 0, st);
-  if (rc) return rc;
-  rc = wdgh_structure_counts(c.rowptr, c.col, n, nnz, c.labels, C, c.plan, plan_host, c.counters, c.node_sum, c.deg,
-                             c.match, c.labels8, n, 0, st);
+  rc = wdgh_spmm_structure_fused(c.rowptr, c.col, n, nnz, c.x, d, d, c.y, d, norm, add_self_loop,
+                                 norm != WDGH_NORM_NONE ? c.dinv : nullptr,
+                                 norm != WDGH_NORM_NONE ? c.deg_code : nullptr, c.labels, C, c.plan, plan_host,
+                                 c.partial, c.counters, c.node_sum, c.deg, c.match, c.labels8, n, 0, 0, st);
   if (rc) return rc;
   WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, sizeof(double), cudaMemcpyDeviceToHost, st));

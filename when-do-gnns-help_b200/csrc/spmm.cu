@@ -21,7 +21,7 @@
 #include <limits.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace wdgh {
 
@@ -211,13 +211,30 @@ spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__rest
 // the float array exceeds L2) is replaced by a 1-byte degree code (n bytes, L2-resident) and a
 // 256-entry table in shared memory that holds bit-identical float values.
 // ---------------------------------------------------------------------------
-template <int NCH, bool HAS_VAL, bool FULL, int MINB>
+// Label statistics fused into the aggregation pass (STATS): the column ids are in registers anyway, so the
+// per-entry label gather (1-byte labels, L2-resident), the match counts (warp ballots + popc) and the
+// class-pair histogram (match_any fold into a shared-memory C x C table) ride along for free while the
+// kernel waits on HBM -- the separate edge pass of wdgh_structure_counts disappears.
+struct StatsArgs {
+  const uint8_t *labels8;        // 1-byte labels by global node id, 0xFF = unlabelled
+  int C;
+  unsigned long long *counters;  // WDGH_SC_* layout
+  int32_t *deg_nsl, *match_nsl;  // per local row
+};
+
+template <int NCH, bool HAS_VAL, bool FULL, int MINB, bool STATS>
 __global__ void __launch_bounds__(32, MINB)
 spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                            const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
                            float *__restrict__ y, int64_t ldy, int norm, int self_loop,
                            const float *__restrict__ dinv, const uint8_t *__restrict__ deg_code, int64_t threshold,
-                           int64_t row_offset) {
+                           int64_t row_offset, StatsArgs sa) {
+  extern __shared__ unsigned s_stats[];  // STATS: [C*C] class-pair histogram, then 4 scalar counters
+  unsigned *s_cnt = s_stats + (STATS ? sa.C * sa.C : 0);
+  if (STATS) {
+    for (int b = threadIdx.x; b < sa.C * sa.C + 4; b += 32) s_stats[b] = 0;
+    __syncwarp();
+  }
   // FULL: d == 128 * NCH, i.e. no column tail and a single column tile -> no per-load predicates
   constexpr int U = (NCH >= 4) ? 2 : (NCH == 2 ? 4 : 8);
   constexpr unsigned kFull = 0xffffffffu;
@@ -249,19 +266,50 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
       e = __ldg(rowptr + r + 1);
     }
   };
-  auto load_seg = [&](int64_t pos, int64_t e, int &j, float &w) {
+  // column ids + weights of the segment [pos, pos+32) of row `r`.  With STATS the label bytes of the row
+  // (lir) and of each neighbour (ljr) are only REQUESTED here; seg_stats() consumes them one pipeline step
+  // later, when they have long arrived, so the statistics never stall the gather stream.
+  auto load_seg = [&](int64_t pos, int64_t e, int64_t r, int &j, float &w, int &lir, int &ljr) {
     j = 0;
     w = 0.f;
     const int64_t idx = pos + lane;
-    if (idx < e) {
+    const bool valid = idx < e;
+    if (valid) {
       j = __ldg(col + idx);
       w = HAS_VAL ? __ldg(val + idx) : 1.f;
+      if (STATS) ljr = __ldg(sa.labels8 + j);
       if (coded) {
         const int c = __ldg(deg_code + j);
         w *= (c < 255) ? table[c] : __ldg(dinv + j);
       } else if (sym) {
         w *= __ldg(dinv + j);
       }
+    }
+    if (STATS && pos < e) lir = __ldg(sa.labels8 + r + row_offset);
+  };
+  // label statistics of one segment whose (j, lir, ljr) were requested earlier; per-row counts go straight
+  // to deg_nsl / match_nsl with one reduction per segment: no row state in registers
+  auto seg_stats = [&](int64_t pos, int64_t e, int64_t r, int j, int lir, int ljr) {
+    if (pos < e) {  // warp-uniform: the segment is not empty
+      const bool valid = pos + lane < e;
+      const int li = (lir == 255) ? -1 : lir;
+      const int lj = (!valid || ljr == 255) ? -1 : ljr;
+      const bool self = valid && ((int64_t)j == r + row_offset);
+      const bool same = valid && (li == lj);
+      const bool both = valid && (li >= 0) && (lj >= 0);
+      const int dn = __popc(__ballot_sync(kFull, valid && !self));
+      const int mn = __popc(__ballot_sync(kFull, same && !self));
+      const unsigned c0 = __popc(__ballot_sync(kFull, same)), c1 = __popc(__ballot_sync(kFull, same && both));
+      const unsigned c2 = __popc(__ballot_sync(kFull, both)), c3 = __popc(__ballot_sync(kFull, self));
+      if (lane == 0) {
+        if (dn) atomicAdd(&sa.deg_nsl[r], dn);
+        if (mn) atomicAdd(&sa.match_nsl[r], mn);
+        if (c0) atomicAdd(&s_cnt[0], c0);
+        if (c1) atomicAdd(&s_cnt[1], c1);
+        if (c2) atomicAdd(&s_cnt[2], c2);
+        if (c3) atomicAdd(&s_cnt[3], c3);
+      }
+      fold_keys((both && !self) ? li * sa.C + lj : -1, s_stats, nullptr, true);
     }
   };
 
@@ -275,7 +323,8 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
   if (heavy1) e1 = s1;
   int j, nj = 0;
   float w, nw = 0.f;
-  load_seg(s, e, j, w);
+  int lir = 255, ljr = 255, nlir = 255, nljr = 255;  // raw label bytes of the current / next row's segment
+  load_seg(s, e, row, j, w, lir, ljr);
 
   while (row < n) {
     bounds(r2, s2, e2);  // two rows ahead
@@ -284,9 +333,10 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     for (int t = 0; t < NCH; ++t) acc[t].zero();
     bool next_issued = false;
     for (int64_t base = s; base < e; base += 32) {
-      if (base != s) load_seg(base, e, j, w);
+      if (base != s) load_seg(base, e, row, j, w, lir, ljr);
       const int cnt = (int)min((int64_t)32, e - base);
       const bool last_seg = base + 32 >= e;
+      bool stats_done = !STATS;
       int k = 0;
       for (; k + U <= cnt; k += U) {  // full batches: U unpredicated gathers in flight
         Vec<4> v[U][NCH];
@@ -299,8 +349,12 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
             else v[u][t].zero();
           }
         }
+        if (!stats_done) {  // this segment's label bytes arrived long ago; its gathers are already in flight
+          seg_stats(base, e, row, j, lir, ljr);
+          stats_done = true;
+        }
         if (!next_issued && last_seg) {  // fetch the next row's ids while this row's gathers are in flight
-          load_seg(s1, e1, nj, nw);
+          load_seg(s1, e1, r1, nj, nw, nlir, nljr);
           next_issued = true;
         }
 #pragma unroll
@@ -322,8 +376,12 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
             else v[u][t].zero();
           }
         }
+        if (!stats_done) {
+          seg_stats(base, e, row, j, lir, ljr);
+          stats_done = true;
+        }
         if (!next_issued && last_seg) {
-          load_seg(s1, e1, nj, nw);
+          load_seg(s1, e1, r1, nj, nw, nlir, nljr);
           next_issued = true;
         }
 #pragma unroll
@@ -336,7 +394,7 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
         }
       }
     }
-    if (!next_issued) load_seg(s1, e1, nj, nw);
+    if (!next_issued) load_seg(s1, e1, r1, nj, nw, nlir, nljr);
     if (!heavy) {
       const int64_t grow = row + row_offset;
       const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
@@ -361,6 +419,16 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     heavy1 = (e1 - s1 > threshold);
     if (heavy1) e1 = s1;
     j = nj; w = nw;
+    lir = nlir; ljr = nljr;
+  }
+  if (STATS) {
+    __syncwarp();
+    unsigned long long *g_hist = sa.counters + WDGH_SC_HEADER + 2 * sa.C;
+    for (int b = lane; b < sa.C * sa.C; b += 32) {
+      const unsigned v = s_stats[b];
+      if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
+    }
+    if (lane < 4 && s_cnt[lane]) atomicAdd(&sa.counters[lane], (unsigned long long)s_cnt[lane]);  // WDGH_SC_MATCH_ALL..N_SELF
   }
 }
 
@@ -579,6 +647,8 @@ struct SpmmArgs {
   const uint8_t *deg_code;
   const int64_t *plan;
   int64_t threshold, n_heavy, n_chunks, row_offset, nnz, n_units;
+  bool stats = false;
+  StatsArgs sa = {nullptr, 0, nullptr, nullptr, nullptr};
   float *partial;
   int64_t ldp;
   cudaStream_t st;
@@ -676,10 +746,18 @@ static int launch_pipelined(const SpmmArgs &a) {
   dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, 128 * NCH));
   const bool full = (a.d == 128 * NCH);
 #define WDGH_PIPE_LAUNCH(FULLV, MINB)                                                                              \
-  spmm_rows_pipelined_kernel<NCH, HAS_VAL, FULLV, MINB><<<grid, 32, 0, a.st>>>(                                       \
+  spmm_rows_pipelined_kernel<NCH, HAS_VAL, FULLV, MINB, false><<<grid, 32, 0, a.st>>>(                                \
       a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
-      a.row_offset)
-  if (full) {
+      a.row_offset, a.sa)
+#define WDGH_PIPE_LAUNCH_STATS(FULLV, MINB)                                                                        \
+  spmm_rows_pipelined_kernel<NCH, false, FULLV, MINB, true><<<grid, 32, (a.sa.C * a.sa.C + 4) * sizeof(unsigned), a.st>>>( \
+      a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
+      a.row_offset, a.sa)
+  if (a.stats) {  // binary adjacency only (checked by the caller)
+    if (full && NCH == 1) WDGH_PIPE_LAUNCH_STATS(true, 32);
+    else if (full) WDGH_PIPE_LAUNCH_STATS(true, 16);
+    else WDGH_PIPE_LAUNCH_STATS(false, 16);
+  } else if (full) {
     switch (minb) {
       case 32: WDGH_PIPE_LAUNCH(true, 32); break;
       case 24: WDGH_PIPE_LAUNCH(true, 24); break;
@@ -689,6 +767,7 @@ static int launch_pipelined(const SpmmArgs &a) {
     WDGH_PIPE_LAUNCH(false, 16);
   }
 #undef WDGH_PIPE_LAUNCH
+#undef WDGH_PIPE_LAUNCH_STATS
   WDGH_LAUNCHED("spmm_rows_pipelined_kernel");
   return 0;
 }
@@ -769,4 +848,60 @@ extern "C" int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const fl
                     (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
                     (partial == nullptr || reinterpret_cast<uintptr_t>(partial) % 16 == 0);
   return val ? dispatch<true>(a, vec4) : dispatch<false>(a, vec4);
+}
+
+extern "C" int wdgh_structure_counts(const int64_t *, const int32_t *, int64_t, int64_t, const int32_t *, int32_t,
+                                     const int64_t *, const int64_t *, int64_t *, double *, int32_t *, int32_t *,
+                                     uint8_t *, int64_t, int64_t, void *);
+
+extern "C" int wdgh_spmm_structure_fused(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
+                                         const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy, int norm,
+                                         int add_self_loop, const float *dinv, const uint8_t *deg_code,
+                                         const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
+                                         const int64_t *plan_host, float *partial, int64_t *counters, double *node_sum,
+                                         int32_t *deg_nsl, int32_t *match_nsl, uint8_t *labels_u8_scratch,
+                                         int64_t n_labels, int64_t row_offset, int single_kernel, void *stream) {
+  WDGH_REQUIRE(rowptr && x && y && labels && plan_i64 && plan_host && counters && node_sum && deg_nsl && match_nsl,
+               "wdgh_spmm_structure_fused: null pointer");
+  WDGH_REQUIRE(n >= 0 && nnz >= 0 && d > 0 && d <= (1 << 24) && ldx >= d && ldy >= d, "wdgh_spmm_structure_fused: bad shape");
+  WDGH_REQUIRE(num_classes >= 1 && num_classes <= 46340, "wdgh_spmm_structure_fused: num_classes out of range");
+  WDGH_REQUIRE(norm == WDGH_NORM_NONE || dinv != nullptr, "wdgh_spmm_structure_fused: norm requires dinv");
+  const int C = num_classes;
+  const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
+                    (partial == nullptr || reinterpret_cast<uintptr_t>(partial) % 16 == 0);
+  // Measured on the B200 (1B-entry graph): the label work inside the aggregation kernel costs more than the
+  // separate 10 ms edge pass (111.3 vs 105.9 ms per step) because the gather kernel is issue- and
+  // power-sensitive, so the single-kernel form is opt-in.
+  const bool fusable = single_kernel != 0 && vec4 && d >= 128 && n > 0 && labels_u8_scratch != nullptr && C <= 254 &&
+                       C * C <= kHistSmemBins && wide_variant() == 1 && n_labels >= n + row_offset;
+  if (!fusable) {  // same results from the two separate passes
+    int rc = wdgh_spmm_csr(rowptr, col, nullptr, n, x, d, ldx, y, ldy, norm, add_self_loop, dinv, deg_code, plan_i64,
+                           plan_host, partial, row_offset, stream);
+    if (rc) return rc;
+    return wdgh_structure_counts(rowptr, col, n, nnz, labels, num_classes, plan_i64, plan_host, counters, node_sum,
+                                 deg_nsl, match_nsl, labels_u8_scratch, n_labels, row_offset, stream);
+  }
+  cudaStream_t st = as_stream(stream);
+  const uint8_t *labels8 = nullptr;
+  int rc = structure_prepare(labels, n_labels, C, labels_u8_scratch, counters, node_sum, &labels8, st);
+  if (rc) return rc;
+  WDGH_CUDA(cudaMemsetAsync(deg_nsl, 0, n * sizeof(int32_t), st));    // per-row counts are accumulated with reductions
+  WDGH_CUDA(cudaMemsetAsync(match_nsl, 0, n * sizeof(int32_t), st));
+  SpmmArgs a;
+  a.rowptr = rowptr; a.col = col; a.val = nullptr; a.n = n; a.x = x; a.d = (int)d; a.ldx = ldx; a.y = y; a.ldy = ldy;
+  a.norm = norm; a.self_loop = add_self_loop ? 1 : 0; a.dinv = dinv; a.deg_code = deg_code; a.plan = plan_i64;
+  a.n_heavy = plan_host[0]; a.n_chunks = plan_host[1]; a.threshold = plan_host[2];
+  a.n_units = plan_host[5]; a.nnz = plan_host[6];
+  a.partial = partial; a.ldp = (d + 3) & ~int64_t(3);
+  a.row_offset = row_offset;
+  a.st = st;
+  a.stats = true;
+  a.sa.labels8 = labels8; a.sa.C = C; a.sa.counters = reinterpret_cast<unsigned long long *>(counters);
+  a.sa.deg_nsl = deg_nsl; a.sa.match_nsl = match_nsl;
+  WDGH_REQUIRE(a.n_chunks == 0 || partial != nullptr, "wdgh_spmm_structure_fused: split rows need the partial buffer");
+  rc = dispatch<false>(a, true);
+  if (rc) return rc;
+  return structure_finish(rowptr, col, n, labels, labels8, C, plan_i64, plan_host, counters, node_sum, deg_nsl,
+                          match_nsl, row_offset, st);
 }

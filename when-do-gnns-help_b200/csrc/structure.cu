@@ -10,25 +10,13 @@
 //                class degree mass (hm.py:141), empty rows, bincount length.
 // HBM traffic per entry: 4 B of `col` plus one label gather that is served by L2 whenever the
 // label array (4 B/node) fits its 126 MB.
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace wdgh {
-
-constexpr int kHistSmemBins = 4096;
 
 struct EdgeAcc {
   unsigned match_all = 0, match_lab = 0, n_lab = 0, n_self = 0;
 };
-
-// Folds one warp-wide batch of class-pair keys (key < 0: nothing to count) into the histogram.
-__device__ __forceinline__ void fold_keys(int key, unsigned *s_hist, unsigned long long *g_hist, bool use_smem) {
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  if (key >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
-    const unsigned c = __popc(peers);
-    if (use_smem) atomicAdd(&s_hist[key], c);
-    else atomicAdd(&g_hist[key], (unsigned long long)c);
-  }
-}
 
 __device__ __forceinline__ void visit(int64_t row, int li, int j, int lj, int C, EdgeAcc &a, int &m_nsl, int &d_nsl,
                                       int &key) {
@@ -146,12 +134,19 @@ structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
 }
 
 // int32 labels -> uint8 (0xFF = negative / unlabelled); requires C <= 254
-__global__ void labels_to_u8_kernel(const int32_t *__restrict__ in, int64_t n, uint8_t *__restrict__ out) {
+// counters[WDGH_SC_N_MULTI_NEG] counts labels < -1: distinct negative labels all map to 0xFF, so their
+// mutual (in)equality (hm.py:51 compares raw labels) is only exact on the int32 path -- the host re-runs it.
+__global__ void labels_to_u8_kernel(const int32_t *__restrict__ in, int64_t n, uint8_t *__restrict__ out,
+                                    unsigned long long *__restrict__ counters) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  long long odd = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int v = in[i];
     out[i] = (v < 0 || v > 254) ? (uint8_t)255 : (uint8_t)v;
+    odd += (v < -1);
   }
+  odd = warp_sum(odd);
+  if ((threadIdx.x & 31) == 0 && odd) atomicAdd(&counters[WDGH_SC_N_MULTI_NEG], (unsigned long long)odd);
 }
 
 // One warp per chunk of a split row.
@@ -329,32 +324,61 @@ static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, con
   return 0;
 }
 
-// rows + chunks passes for one label representation
+// per-row edge pass for one label representation
 template <typename L>
-static int launch_edge_passes(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz, const L *labels, int C,
-                              const int64_t *plan_i64, const int64_t *plan_host, unsigned long long *cnt,
-                              int32_t *deg_nsl, int32_t *match_nsl, size_t hist_smem, cudaStream_t st,
-                              int64_t row_offset) {
-  const int64_t threshold = plan_host[2], n_chunks = plan_host[1];
+static int launch_edge_rows(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz, const L *labels, int C,
+                            int64_t threshold, unsigned long long *cnt, int32_t *deg_nsl, int32_t *match_nsl,
+                            size_t hist_smem, cudaStream_t st, int64_t row_offset) {
   const double avg = (double)nnz / (double)n;
-  int rc;
   // 4 entries per lane and iteration: pick G so that one iteration covers a typical row
-  if (avg <= 16.0) rc = launch_rows<4, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else if (avg <= 48.0) rc = launch_rows<8, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else if (avg <= 96.0) rc = launch_rows<16, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else rc = launch_rows<32, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  if (rc) return rc;
-  if (n_chunks > 0) {
-    structure_chunks_kernel<L><<<persistent_grid(ceil_div(n_chunks, 8), 8), 256, hist_smem, st>>>(
-        rowptr, col, labels, C, plan_i64, n_chunks, cnt, deg_nsl, match_nsl, row_offset);
-    WDGH_LAUNCHED("structure_chunks_kernel");
-  }
-  return 0;
+  if (avg <= 16.0) return launch_rows<4, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  if (avg <= 48.0) return launch_rows<8, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  if (avg <= 96.0) return launch_rows<16, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  return launch_rows<32, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
 }
 
 }  // namespace wdgh
 
 using namespace wdgh;
+
+int wdgh::structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint8_t *labels_u8_scratch,
+                            int64_t *counters, double *node_sum, const uint8_t **labels8_out, cudaStream_t st) {
+  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
+  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
+  *labels8_out = nullptr;
+  if (labels_u8_scratch != nullptr && C <= 254 && n_labels > 0) {
+    labels_to_u8_kernel<<<persistent_grid(ceil_div(n_labels, 256), 8), 256, 0, st>>>(
+        labels, n_labels, labels_u8_scratch, reinterpret_cast<unsigned long long *>(counters));
+    WDGH_LAUNCHED("labels_to_u8_kernel");
+    *labels8_out = labels_u8_scratch;
+  }
+  return 0;
+}
+
+int wdgh::structure_finish(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels,
+                           const uint8_t *labels8, int C, const int64_t *plan_i64, const int64_t *plan_host,
+                           int64_t *counters, double *node_sum, int32_t *deg_nsl, int32_t *match_nsl,
+                           int64_t row_offset, cudaStream_t st) {
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
+  const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
+  const int64_t n_chunks = plan_host[1];
+  if (n_chunks > 0) {
+    const unsigned grid = persistent_grid(ceil_div(n_chunks, 8), 8);
+    if (labels8)
+      structure_chunks_kernel<uint8_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels8, C, plan_i64, n_chunks, cnt,
+                                                                    deg_nsl, match_nsl, row_offset);
+    else
+      structure_chunks_kernel<int32_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels, C, plan_i64, n_chunks, cnt,
+                                                                    deg_nsl, match_nsl, row_offset);
+    WDGH_LAUNCHED("structure_chunks_kernel");
+  }
+  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
+  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
+                                                                                     match_nsl, cnt, node_sum, row_offset);
+  WDGH_LAUNCHED("structure_nodes_kernel");
+  return 0;
+}
 
 extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                                      const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
@@ -368,28 +392,17 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   WDGH_REQUIRE(labels_u8_scratch == nullptr || n_labels >= n + row_offset, "wdgh_structure_counts: n_labels too small");
   cudaStream_t st = as_stream(stream);
   const int C = num_classes;
-  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
-  WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
-  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
-  if (n == 0) return 0;
+  const uint8_t *labels8 = nullptr;
+  int rc = structure_prepare(labels, n == 0 ? 0 : n_labels, C, labels_u8_scratch, counters, node_sum, &labels8, st);
+  if (rc || n == 0) return rc;
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
   const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
-  int rc;
-  if (labels_u8_scratch != nullptr && C <= 254) {
-    labels_to_u8_kernel<<<persistent_grid(ceil_div(n_labels, 256), 8), 256, 0, st>>>(labels, n_labels, labels_u8_scratch);
-    WDGH_LAUNCHED("labels_to_u8_kernel");
-    rc = launch_edge_passes<uint8_t>(rowptr, col, n, nnz, labels_u8_scratch, C, plan_i64, plan_host, cnt, deg_nsl,
-                                     match_nsl, hist_smem, st, row_offset);
-  } else {
-    rc = launch_edge_passes<int32_t>(rowptr, col, n, nnz, labels, C, plan_i64, plan_host, cnt, deg_nsl, match_nsl,
-                                     hist_smem, st, row_offset);
-  }
+  const int64_t threshold = plan_host[2];
+  if (labels8) rc = launch_edge_rows<uint8_t>(rowptr, col, n, nnz, labels8, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  else rc = launch_edge_rows<int32_t>(rowptr, col, n, nnz, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
   if (rc) return rc;
-  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
-  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
-                                                                                     match_nsl, cnt, node_sum, row_offset);
-  WDGH_LAUNCHED("structure_nodes_kernel");
-  return 0;
+  return structure_finish(rowptr, col, n, labels, labels8, C, plan_i64, plan_host, counters, node_sum, deg_nsl,
+                          match_nsl, row_offset, st);
 }
 
 extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,

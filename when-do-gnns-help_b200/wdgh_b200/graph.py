@@ -278,7 +278,51 @@ def structure_counts_raw(g: CSRGraph, labels32, num_classes, scratch=None):
 
 def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
     counters, node_sum, deg, match, _ = structure_counts_raw(g, labels32, num_classes)
+    if int(counters[_lib.SC_N_MULTI_NEG].item()):
+        # several distinct negative labels: the 1-byte label copy folds them together, redo on int32 labels
+        c = int(num_classes)
+        scratch = (counters, node_sum, deg, match, None)
+        counters, node_sum, deg, match, _ = structure_counts_raw(g, labels32, c, scratch)
     return _unpack_counts(g.n, g.nnz, int(num_classes), counters, node_sum, deg, match)
+
+
+def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, add_self_loop=True, out=None,
+                         dinv=None, deg_code=None, scratch=None, single_kernel=False):
+    """One call: y = norm(A [+I]) x and the label statistics (device tensors, no sync).
+
+    single_kernel=True folds the label pass into the aggregation kernel (same results, measured slower).
+
+    Returns (y, (counters, node_sum, deg, match, labels_u8)); binary adjacency only."""
+    if g.val is not None:
+        raise ValueError("the fused pass needs a binary adjacency (values = None)")
+    x = _cuda(x, torch.float32)
+    d = int(x.shape[1])
+    c = int(num_classes)
+    dev = g.device
+    y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=dev)
+    n_labels = int(labels32.shape[0])
+    if scratch is None:
+        scratch = (torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev),
+                   torch.empty(1, dtype=torch.float64, device=dev),
+                   torch.empty(g.n, dtype=torch.int32, device=dev),
+                   torch.empty(g.n, dtype=torch.int32, device=dev),
+                   torch.empty(n_labels, dtype=torch.uint8, device=dev))
+    counters, node_sum, deg, match, lab8 = scratch
+    plan, plan_host = g.plan
+    ldp = (d + 3) & ~3
+    n_part = max(g.n_chunks, 2 * g.n_units) * ldp
+    partial = g._partial.get(n_part)
+    if partial is None and n_part:
+        partial = torch.empty(n_part, dtype=torch.float32, device=dev)
+        g._partial = {n_part: partial}
+    if norm != NORM_NONE and dinv is None:
+        dinv, _, deg_code = g.degree_scale(norm, add_self_loop)
+    check(lib.wdgh_spmm_structure_fused(ptr(g.rowptr), ptr(g.col), g.n, g.nnz, ptr(x), d, x.stride(0), ptr(y),
+                                        y.stride(0), norm, int(bool(add_self_loop)), ptr(dinv), ptr(deg_code),
+                                        ptr(labels32), c, ptr(plan), plan_host, ptr(partial), ptr(counters),
+                                        ptr(node_sum), ptr(deg), ptr(match), ptr(lab8), n_labels, g.row_offset,
+                                        int(bool(single_kernel)), stream_ptr()), "wdgh_spmm_structure_fused")
+    return y, scratch
 
 
 def structure_counts_coo(edge_index, n, labels32, num_classes) -> StructureCounts:

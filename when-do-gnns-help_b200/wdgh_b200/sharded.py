@@ -129,6 +129,7 @@ class CudaShardedStats(ShardedStats):
         super().__init__(part, rank, x_local, labels32_local, num_classes, group)
         self._scratch = None
         self._y = None
+        self._x_full = None
 
     def local_degree_scale(self, norm, add_self_loop):
         self.g._dinv.clear()  # recomputed every step: it is part of the timed path
@@ -139,6 +140,34 @@ class CudaShardedStats(ShardedStats):
         G = self._G
         if self._y is None or self._y.shape[1] != x_full.shape[1]:
             self._y = torch.empty((self.g.n, x_full.shape[1]), dtype=torch.float32, device=x_full.device)
-        y = G.spmm(self.g, x_full, norm, add_self_loop, out=self._y, dinv=dinv_full, deg_code=self.code_full)
-        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)
+        y, self._scratch = G.spmm_structure_fused(self.g, x_full, labels_full, self.c, norm, add_self_loop,
+                                                  out=self._y, dinv=dinv_full, deg_code=self.code_full,
+                                                  scratch=self._scratch)
         return y, self._scratch[0], self._scratch[1]
+
+    def step(self, norm=_lib.NORM_SYM, add_self_loop=True):
+        """Same result as ShardedStats.step, with the feature all-gather (the only large transfer:
+        (N-1)/N of the feature matrix per rank over NVLink) issued asynchronously so that the label pass,
+        which needs only the gathered labels, runs underneath it."""
+        G = self._G
+        labels_full = _all_gather_rows(self.labels_local, self.group)
+        dinv_full = None
+        self.code_full = None
+        if norm != _lib.NORM_NONE:
+            dinv, code = self.local_degree_scale(norm, add_self_loop)
+            dinv_full = _all_gather_rows(_pad_rows(dinv, self.part.block), self.group)
+            if code is not None:
+                self.code_full = _all_gather_rows(_pad_rows(code, self.part.block), self.group)
+        world = dist.get_world_size(self.group)
+        shape = (world * self.x_local.shape[0],) + tuple(self.x_local.shape[1:])
+        if self._x_full is None or tuple(self._x_full.shape) != shape:
+            self._x_full = self.x_local.new_empty(shape)
+        work = dist.all_gather_into_tensor(self._x_full, self.x_local.contiguous(), group=self.group, async_op=True)
+        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)  # overlaps the gather
+        work.wait()
+        d = int(self._x_full.shape[1])
+        if self._y is None or self._y.shape[1] != d:
+            self._y = torch.empty((self.g.n, d), dtype=torch.float32, device=self._x_full.device)
+        y = G.spmm(self.g, self._x_full, norm, add_self_loop, out=self._y, dinv=dinv_full, deg_code=self.code_full)
+        counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
+        return y, counters, node_sum
