@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--classes", type=int, default=10)
     ap.add_argument("--homophily", type=float, default=0.3)
     ap.add_argument("--cpu-sample-nodes", type=int, default=1_000_000)
+    ap.add_argument("--slabs", type=int, default=0, help="feature column slabs for the N>1 pipeline (0 = default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -106,7 +107,7 @@ def gen_rows(r0, r1, n, avg_deg, C, h, d, device, seed=1234, want_x=True):
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, device):
         self.proc = None
@@ -114,7 +115,7 @@ class ClockSampler:
             uuid = str(torch.cuda.get_device_properties(device).uuid)
             sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -134,9 +135,12 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in text.strip().splitlines():
             f = [v.strip() for v in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
+                busy = float(f[7]) > 0  # the sampler starts before the warm-up: keep the samples taken under load
+                if not busy:
+                    continue
                 sm.append(float(f[0])), mx.append(float(f[1]))
             except ValueError:
                 continue
@@ -250,7 +254,7 @@ def main():
                                                    deg_code=code, scratch=scratch[0])
             return scratch[0][0], scratch[0][1]
     else:
-        pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C)
+        pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C, slabs=(args.slabs or None))
 
         def step():
             _, counters, node_sum = pipe.step(W.NORM_SYM, True)
@@ -261,10 +265,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(device)  # samples with utilisation > 0 = warm-up + timed steps (both under load)
     for _ in range(max(args.warmup, 3)):
         counters, node_sum = step()
     barrier()
-    sampler = ClockSampler(device)
     launches0 = W.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -289,7 +293,7 @@ def main():
     else:
         xs, _, dinv = pipe.gather_inputs(W.NORM_SYM, True)
         code = pipe.code_full
-        ys = pipe._y
+        ys = torch.empty((g.n, d), dtype=torch.float32, device=device)
     for _ in range(2):
         G.spmm(g, xs, W.NORM_SYM, True, out=ys, dinv=dinv, deg_code=code)
     torch.cuda.synchronize()

@@ -416,3 +416,60 @@ def test_empty_graph(W):
     s = W.graph.structure_counts(g, lab32, 2)
     assert s.match_all == 0 and s.hist.sum() == 0 and s.n_empty == 5
     assert torch.isnan(W.homophily_metrics.edge_homophily(g, torch.tensor([0, 1, 0, 1, 1])))
+
+
+# ---------------------------------------------------------------------------
+# LINKX-scale graphs (BASELINE.json configs[2], configs[3]) against the oracle, every metric end to end
+# ---------------------------------------------------------------------------
+def _linkx_like(n, avg, c, seed, neg_frac, hubs):
+    rng = np.random.default_rng(seed)
+    deg = np.minimum((rng.pareto(1.6, n) + 1) * avg / 2.7, n // 3).astype(np.int64)
+    deg[:hubs] = n // 4                      # genius / Penn94-style hubs -> split rows
+    src = np.repeat(np.arange(n), deg)
+    dst = rng.integers(0, n, src.shape[0])
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    row, col, _ = O.coalesce(np.concatenate([src, dst]), np.concatenate([dst, src]), None, n)  # to_undirected
+    labels = rng.integers(0, c, n).astype(np.int64)
+    labels[:c] = np.arange(c)
+    if neg_frac:
+        labels[rng.random(n) < neg_frac] = -1
+    return row, col, labels
+
+
+@pytest.mark.parametrize("name,n,avg,c,neg,hubs,d", [
+    ("twitch-gamer-like", 168_114, 20, 2, 0.0, 0, 7),       # 168k nodes, ~6.8M entries, 2 classes
+    ("penn94-like", 41_554, 32, 2, 0.2, 4, 5),              # -1 = unlabelled nodes
+    ("genius-like", 421_961, 2, 2, 0.0, 12, 12),            # extreme skew, many degree-1 nodes
+])
+def test_linkx_scale_metrics_vs_oracle(W, name, n, avg, c, neg, hubs, d):
+    uf, hm = W.util_funcs, W.homophily_metrics
+    row, col, labels = _linkx_like(n, avg, c, seed=len(name), neg_frac=neg, hubs=hubs)
+    x = np.random.default_rng(3).standard_normal((n, d)).astype(np.float32)
+    ones = np.ones(row.shape[0], np.float32)
+    A_raw = sparse(row, col, ones, n)
+    lab_t = torch.from_numpy(labels)
+    for sym, fn, ofn in ((1, uf.sys_normalized_adjacency, O.sys_normalized_adjacency),
+                         (0, uf.row_normalized_adjacency, O.row_normalized_adjacency)):
+        gn = fn(A_raw)                                   # homophily_tests.py:99-104
+        r2, c2, v2 = ofn(row, col, ones, n)
+        A = uf.sparse_mx_to_torch_sparse_tensor(gn)
+        assert np.array_equal(A.indices().cpu().numpy(), np.vstack([r2, c2]))
+        close(A.values(), v2, rtol=1e-6)
+        check_counts_exact(W, gn, labels, r2, c2, n)
+        close(hm.edge_homophily(gn, lab_t), O.edge_homophily(r2, c2, labels), rtol=1e-6)
+        close(hm.node_homophily(gn, lab_t), O.node_homophily(r2, c2, labels, n), rtol=1e-5)
+        close(hm.our_measure(A.indices(), lab_t), O.class_homophily(r2, c2, labels), rtol=1e-4, atol=1e-7)
+        close(hm.adjusted_homo(gn, lab_t), O.adjusted_homo(r2, c2, labels, n), rtol=RTOL, atol=1e-6)
+        close(hm.label_informativeness(gn, lab_t), O.label_informativeness(r2, c2, labels, n), rtol=RTOL, atol=1e-5)
+        y = W.spmm(gn, torch.from_numpy(x)).cpu().numpy()
+        ref = O.spmm(r2, c2, v2, n, x)
+        np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * np.abs(ref).max())
+        y2 = uf.propagate(A_raw, torch.from_numpy(x), symmetric=sym).cpu().numpy()   # on-the-fly form
+        np.testing.assert_allclose(y2, ref, rtol=RTOL, atol=1e-5 * np.abs(ref).max())
+    # generalised edge homophily, sampled branch with the reference's default sample_max (nnz >= 75000)
+    random.seed(5)
+    got = hm.generalized_edge_homophily(A_raw, torch.from_numpy(x), lab_t, sample_max=75000, iteration=3)
+    random.seed(5)
+    want = O.generalized_edge_homophily(row, col, x, n, sample_max=75000, iteration=3)
+    close(got, want, rtol=RTOL, atol=1e-6)

@@ -46,6 +46,24 @@ struct Vec<4> {
   __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
 };
 template <>
+struct Vec<2> {
+  float2 v;
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void load(const float *p) {
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  }
+  __device__ __forceinline__ void fma(float w, const Vec &o) {
+    v.x = fmaf(w, o.v.x, v.x);
+    v.y = fmaf(w, o.v.y, v.y);
+  }
+  __device__ __forceinline__ void add(const Vec &o) { v.x += o.v.x; v.y += o.v.y; }
+  __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; }
+  __device__ __forceinline__ void store_stream(float *p) const {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+  }
+  __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float2 *>(p) = v; }
+};
+template <>
 struct Vec<1> {
   float v;
   __device__ __forceinline__ void zero() { v = 0.f; }
@@ -222,7 +240,7 @@ struct StatsArgs {
   int32_t *deg_nsl, *match_nsl;  // per local row
 };
 
-template <int NCH, bool HAS_VAL, bool FULL, int MINB, bool STATS>
+template <int VEC, int NCH, bool HAS_VAL, bool FULL, int MINB, bool STATS>
 __global__ void __launch_bounds__(32, MINB)
 spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                            const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
@@ -235,8 +253,12 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     for (int b = threadIdx.x; b < sa.C * sa.C + 4; b += 32) s_stats[b] = 0;
     __syncwarp();
   }
-  // FULL: d == 128 * NCH, i.e. no column tail and a single column tile -> no per-load predicates
-  constexpr int U = (NCH >= 4) ? 2 : (NCH == 2 ? 4 : 8);
+  // One warp per row: lane l owns VEC contiguous floats of NCH chunks (VEC = 4: d >= 128; VEC = 2: d = 64;
+  // VEC = 1: d = 32 -- the narrow forms serve the column-slab pipelines that overlap transfers with compute).
+  // FULL: d == 32 * VEC * NCH, i.e. no column tail and a single column tile -> no per-load predicates
+  constexpr int TILE = 32 * VEC * NCH;
+  constexpr int U0 = 32 / (VEC * NCH);  // independent row gathers in flight per lane (16 B x 8 for d = 128)
+  constexpr int U = U0 > 16 ? 16 : (U0 < 2 ? 2 : U0);
   constexpr unsigned kFull = 0xffffffffu;
   __shared__ float table[256];
   const int lane = threadIdx.x;
@@ -250,13 +272,13 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     }
     __syncwarp();
   }
-  const int cbase = FULL ? 0 : blockIdx.y * (128 * NCH);
+  const int cbase = FULL ? 0 : blockIdx.y * TILE;
   bool live[NCH];
 #pragma unroll
-  for (int t = 0; t < NCH; ++t) live[t] = FULL || (cbase + (t * 32 + lane) * 4 < d);
+  for (int t = 0; t < NCH; ++t) live[t] = FULL || (cbase + (t * 32 + lane) * VEC < d);
   const int64_t W = gridDim.x;
   const int ld32 = (int)ldx;                       // row stride in floats (< 2^31): one IMAD.WIDE per gather
-  const float *xl = x + cbase + lane * 4;          // this lane's column slice of row 0
+  const float *xl = x + cbase + lane * VEC;        // this lane's column slice of row 0
 
   auto bounds = [&](int64_t r, int64_t &s, int64_t &e) {
     s = 0;
@@ -328,7 +350,7 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
 
   while (row < n) {
     bounds(r2, s2, e2);  // two rows ahead
-    Vec<4> acc[NCH];
+    Vec<VEC> acc[NCH];
 #pragma unroll
     for (int t = 0; t < NCH; ++t) acc[t].zero();
     bool next_issued = false;
@@ -339,13 +361,13 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
       bool stats_done = !STATS;
       int k = 0;
       for (; k + U <= cnt; k += U) {  // full batches: U unpredicated gathers in flight
-        Vec<4> v[U][NCH];
+        Vec<VEC> v[U][NCH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const float *xr = xl + (int64_t)__shfl_sync(kFull, j, k + u) * ld32;
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
-            if (live[t]) v[u][t].load(xr + t * 128);
+            if (live[t]) v[u][t].load(xr + t * (32 * VEC));
             else v[u][t].zero();
           }
         }
@@ -365,14 +387,14 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
         }
       }
       if (k < cnt) {  // tail batch, predicated
-        Vec<4> v[U][NCH];
+        Vec<VEC> v[U][NCH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool on = k + u < cnt;
           const float *xr = xl + (int64_t)__shfl_sync(kFull, j, on ? k + u : 0) * ld32;
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
-            if (on && live[t]) v[u][t].load(xr + t * 128);
+            if (on && live[t]) v[u][t].load(xr + t * (32 * VEC));
             else v[u][t].zero();
           }
         }
@@ -402,9 +424,9 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
 #pragma unroll
       for (int t = 0; t < NCH; ++t) {
         if (live[t]) {
-          const int c = cbase + (t * 32 + lane) * 4;
+          const int c = cbase + (t * 32 + lane) * VEC;
           if (self_loop) {
-            Vec<4> xi;
+            Vec<VEC> xi;
             xi.load(x + grow * ldx + c);
             acc[t].fma(self_w, xi);
           }
@@ -738,22 +760,24 @@ static int pipelined_minb() {
   return cached;
 }
 
-template <int NCH, bool HAS_VAL>
+template <int VEC, int NCH, bool HAS_VAL>
 static int launch_pipelined(const SpmmArgs &a) {
+  constexpr int TILE = 32 * VEC * NCH;
   const int minb = (NCH == 1) ? pipelined_minb() : 16;
   int64_t ctas = (int64_t)sm_count() * minb;
   if (ctas > a.n) ctas = a.n;
-  dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, 128 * NCH));
-  const bool full = (a.d == 128 * NCH);
+  dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, TILE));
+  const bool full = (a.d == TILE);
 #define WDGH_PIPE_LAUNCH(FULLV, MINB)                                                                              \
-  spmm_rows_pipelined_kernel<NCH, HAS_VAL, FULLV, MINB, false><<<grid, 32, 0, a.st>>>(                                \
+  spmm_rows_pipelined_kernel<VEC, NCH, HAS_VAL, FULLV, MINB, false><<<grid, 32, 0, a.st>>>(                           \
       a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
       a.row_offset, a.sa)
 #define WDGH_PIPE_LAUNCH_STATS(FULLV, MINB)                                                                        \
-  spmm_rows_pipelined_kernel<NCH, false, FULLV, MINB, true><<<grid, 32, (a.sa.C * a.sa.C + 4) * sizeof(unsigned), a.st>>>( \
-      a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
-      a.row_offset, a.sa)
-  if (a.stats) {  // binary adjacency only (checked by the caller)
+  spmm_rows_pipelined_kernel<4, NCH, false, FULLV, MINB, true>                                                        \
+      <<<grid, 32, (a.sa.C * a.sa.C + 4) * sizeof(unsigned), a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, \
+                                                                      a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, \
+                                                                      a.threshold, a.row_offset, a.sa)
+  if (a.stats && VEC == 4) {  // binary adjacency only (checked by the caller)
     if (full && NCH == 1) WDGH_PIPE_LAUNCH_STATS(true, 32);
     else if (full) WDGH_PIPE_LAUNCH_STATS(true, 16);
     else WDGH_PIPE_LAUNCH_STATS(false, 16);
@@ -776,10 +800,12 @@ template <bool HAS_VAL>
 static int dispatch(const SpmmArgs &a, bool vec4) {
   int rc;
   const int d = a.d;
-  if (vec4 && d >= 128 && wide_variant() == 1) {
-    if (d <= 128) rc = launch_pipelined<1, HAS_VAL>(a);
-    else if (d <= 256) rc = launch_pipelined<2, HAS_VAL>(a);
-    else rc = launch_pipelined<4, HAS_VAL>(a);
+  if (vec4 && (d >= 128 || d == 64 || d == 32) && wide_variant() == 1) {
+    if (d == 32) rc = launch_pipelined<1, 1, HAS_VAL>(a);
+    else if (d == 64) rc = launch_pipelined<2, 1, HAS_VAL>(a);
+    else if (d <= 128) rc = launch_pipelined<4, 1, HAS_VAL>(a);
+    else if (d <= 256) rc = launch_pipelined<4, 2, HAS_VAL>(a);
+    else rc = launch_pipelined<4, 4, HAS_VAL>(a);
     if (rc) return rc;
     if (d <= 128) return launch_heavy<4, 1, HAS_VAL>(a);
     if (d <= 256) return launch_heavy<4, 2, HAS_VAL>(a);

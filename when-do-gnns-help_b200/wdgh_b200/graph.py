@@ -187,6 +187,8 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
         raise ValueError(f"features must be [n={g.n_global}, d], got {tuple(x.shape)}")
     d = int(x.shape[1])
     y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=g.device)
+    if y.shape != (g.n, d) or y.stride(1) != 1:
+        raise ValueError("out must be [n, d] with unit column stride (a column slab of a wider matrix is fine)")
     plan, plan_host = g.plan
     ldp = (d + 3) & ~3
     n_part = max(g.n_chunks, 2 * g.n_units) * ldp  # scratch for rows split across chunks / stream units

@@ -120,16 +120,31 @@ class ShardedStats:
 class CudaShardedStats(ShardedStats):
     """The product: local compute = the CUDA kernels of libwdgh_b200.so on this rank's GPU."""
 
-    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None):
+    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None, slabs=None):
         from . import graph as G
         self._G = G
         self.g = graph_local
+        d = int(x_local.shape[1])
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if slabs is None:
+            # Column slabs of the feature matrix (gather of slab s+1 overlapping the aggregation of slab s) are
+            # supported but OFF: measured on 2 x B200, 1B-entry graph, d = 128: 1 slab 76.2 ms, 2 slabs 91.2 ms,
+            # 4 slabs 130.6 ms per step -- the gather kernel is bound by the number of random row requests, not
+            # by their size, so every extra slab costs almost a full aggregation pass.
+            slabs = 1
+        if d % slabs or (d // slabs) % 32:
+            raise ValueError("feature width must split into slabs that are multiples of 32 columns")
+        self.slabs = int(slabs)
         if graph_local.row_offset != part.bounds(rank)[0] or graph_local.n != part.rows(rank):
             raise ValueError("graph shard does not match the partition")
         super().__init__(part, rank, x_local, labels32_local, num_classes, group)
         self._scratch = None
         self._y = None
         self._x_full = None
+        # slab-major copy of the local feature rows: each slab is one contiguous all-gather payload
+        ds = d // self.slabs
+        self._x_slabs = ([self.x_local] if self.slabs == 1 else
+                         [self.x_local[:, k * ds:(k + 1) * ds].contiguous() for k in range(self.slabs)])
 
     def local_degree_scale(self, norm, add_self_loop):
         self.g._dinv.clear()  # recomputed every step: it is part of the timed path
@@ -159,15 +174,20 @@ class CudaShardedStats(ShardedStats):
             if code is not None:
                 self.code_full = _all_gather_rows(_pad_rows(code, self.part.block), self.group)
         world = dist.get_world_size(self.group)
-        shape = (world * self.x_local.shape[0],) + tuple(self.x_local.shape[1:])
-        if self._x_full is None or tuple(self._x_full.shape) != shape:
-            self._x_full = self.x_local.new_empty(shape)
-        work = dist.all_gather_into_tensor(self._x_full, self.x_local.contiguous(), group=self.group, async_op=True)
-        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)  # overlaps the gather
-        work.wait()
-        d = int(self._x_full.shape[1])
+        d = int(self.x_local.shape[1])
+        ds = d // self.slabs
+        if self._x_full is None:
+            self._x_full = [xs.new_empty((world * xs.shape[0], ds)) for xs in self._x_slabs]
+        # all slab gathers are queued back to back on the collective stream ...
+        works = [dist.all_gather_into_tensor(buf, xs, group=self.group, async_op=True)
+                 for buf, xs in zip(self._x_full, self._x_slabs)]
+        # ... the label pass and then the aggregation of slab s run while slab s+1 is still in flight
+        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)
         if self._y is None or self._y.shape[1] != d:
-            self._y = torch.empty((self.g.n, d), dtype=torch.float32, device=self._x_full.device)
-        y = G.spmm(self.g, self._x_full, norm, add_self_loop, out=self._y, dinv=dinv_full, deg_code=self.code_full)
+            self._y = torch.empty((self.g.n, d), dtype=torch.float32, device=self.x_local.device)
+        for k, (work, buf) in enumerate(zip(works, self._x_full)):
+            work.wait()
+            G.spmm(self.g, buf, norm, add_self_loop, out=self._y[:, k * ds:(k + 1) * ds], dinv=dinv_full,
+                   deg_code=self.code_full)
         counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
-        return y, counters, node_sum
+        return self._y, counters, node_sum
