@@ -330,8 +330,8 @@ def main():
     # ---- metrics of the last step (sanity; also proves the counters left the device) ----------------
     h = counters.cpu().numpy()
     metrics = {"edge_homophily_with_self_loops": float((h[0] + n) / (nnz + n)),
-               "node_homophily": float(node_sum.item() / max(int(h[G._lib.SC_N_NODES_NSL]), 1)),
-               "class_pair_hist_total": int(h[G._lib.SC_HEADER + 2 * C:].sum())}
+               "node_homophily": float(node_sum[0].item() / max(int(h[G._lib.SC_N_NODES_NSL]), 1)),
+               "class_pair_hist_total": int(h[G._lib.SC_HEADER + 2 * C:G._lib.SC_HEADER + 2 * C + C * C].sum())}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
     e2e = None
@@ -382,11 +382,11 @@ def run_e2e(args, W, G, world, rank, device, g, x_local, labels_local, nnz, part
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": f"host staging failed: {str(e)[:80]}"}
     h2d = rowptr_h.numel() * 8 + col_h.numel() * 4 + x_h.numel() * 4 + lab_h.numel() * 4
-    n_cnt = G._lib.SC_HEADER + 2 * C + C * C
-    d2h = n_cnt * 8 + 8
+    n_cnt = G._lib.sc_words(C)
+    d2h = n_cnt * 8 + 16
     if world == 1:
         counters_h = torch.zeros(n_cnt, dtype=torch.int64).pin_memory()
-        node_sum_h = torch.zeros(1, dtype=torch.float64).pin_memory()
+        node_sum_h = torch.zeros(2, dtype=torch.float64).pin_memory()
 
         def once():
             W._lib.check(lib.wdgh_pipeline_host(rowptr_h.data_ptr(), col_h.data_ptr(), n, g.nnz, x_h.data_ptr(), d,

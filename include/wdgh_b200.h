@@ -128,7 +128,7 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
 /* ---- label metrics: one pass over the edges ------------------------------ */
 /* Integer statistics every label metric of homophily_metrics.py is a ratio of
  * (edge / node / class / adjusted homophily, label informativeness; hm.py:43-161).
- *   counters int64[WDGH_SC_HEADER + 2*C + C*C], zeroed by the call:
+ *   counters int64[WDGH_SC_WORDS(C)], zeroed by the call:
  *     [WDGH_SC_MATCH_ALL]  stored entries with equal endpoint labels (self-loops included)   hm.py:51
  *     [WDGH_SC_MATCH_LAB]  same, both endpoints labelled >= 0                               hm.py:52-54
  *     [WDGH_SC_N_LAB]      stored entries with both endpoints labelled >= 0
@@ -139,7 +139,10 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
  *     [WDGH_SC_HEADER + c]           nodes of class c                                        hm.py:114,137
  *     [WDGH_SC_HEADER + C + c]       sum over class-c nodes of stored entries per row        hm.py:141
  *     [WDGH_SC_HEADER + 2C + a*C+b]  off-diagonal entries a->b, both labelled                hm.py:97-100,144
- *   node_sum double[1]: sum_i f32(match_i)/f32(deg_i) over rows with deg_i > 0 (off-diagonal)  hm.py:77-78
+ *     [WDGH_SC_HEADER + 2C + C*C + c] class-c nodes without any off-diagonal entry (homophily_plot.py our_measure :131-132)
+ *   node_sum double[2]: [0] sum_i f32(match_i)/f32(deg_i) over rows with deg_i > 0, diagonal excluded (hm.py:77-78);
+ *                       [1] the same with the stored diagonal counted as a matching entry
+ *                           (utils/homophily_plot.py:92-100, which does not strip self-loops)
  *   deg_nsl / match_nsl int32[n]: per-row off-diagonal entry count / label matches (scratch AND output)
  */
 #define WDGH_SC_MATCH_ALL   0
@@ -151,6 +154,7 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
 #define WDGH_SC_N_NODES_NSL 6
 #define WDGH_SC_N_MULTI_NEG 7 /* labels < -1 seen while packing to 1 byte: re-run without labels_u8_scratch */
 #define WDGH_SC_HEADER      8
+#define WDGH_SC_WORDS(C)    (WDGH_SC_HEADER + 3 * (C) + (C) * (C))
 int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                           const int32_t *labels, int32_t num_classes,
                           const int64_t *plan_i64, const int64_t *plan_host,
@@ -181,7 +185,9 @@ int wdgh_spmm_structure_fused(const int64_t *rowptr, const int32_t *col, int64_t
 int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,
                               const int32_t *labels, int32_t num_classes,
                               int64_t *counters, double *node_sum,
-                              int32_t *deg_nsl, int32_t *match_nsl, void *stream);
+                              int32_t *deg_nsl, int32_t *match_nsl,
+                              int hist_includes_self_loops /* homophily_plot.py compact_matrix_edge_idx keeps (i,i) */,
+                              void *stream);
 /* edge_homophily with a 2-D label matrix (hm.py:50-56 as called from
  * homophily_tests.py:115-116): counts elementwise-equal label entries over all
  * stored (i,j); *equal_count (device uint64) out of nnz*c comparisons. */
@@ -190,7 +196,9 @@ int wdgh_edge_label_rows_equal(const int64_t *rowptr, const int32_t *col, int64_
                                unsigned long long *equal_count, void *stream);
 
 /* ---- generalised edge homophily: feature cosine over edges (hm.py:164-187) */
-/* mode 0: all off-diagonal stored entries whose value is > 0 (val NULL = all);
+/* mode bit 1 (value 2) set: plain dot products <x_i, x_j> instead of cosines (homophily_plot.py:48-52
+ * edge_homophily with a label matrix).
+ * mode 0: all off-diagonal stored entries whose value is > 0 (val NULL = all);
  *         out_sum[0] += sum of cosines, out_cnt[0] += entries counted.
  * mode 1: the `n_ids` stored-entry ids in `entry_ids` (position in the coalesced COO,
  *         diagonal included); same outputs.  NaN cosines count as 0 (hm.py:168,185). */
@@ -218,6 +226,8 @@ int wdgh_class_colsum(const float *g, int64_t m, int64_t ldg, const int32_t *lab
  * scratch_c: float32[C]. */
 int wdgh_las_score(const float *w, const int32_t *labels, const float *label_rows, int64_t m, int32_t num_classes,
                    int hard, int lp, int is_sum, float *scratch_c, unsigned long long *count, void *stream);
+/* in place: g <- k (pi - acos k) / (2 pi) with k = clamp(g, 0, 1)   (homophily_plot.py similarity NTK branch :191-193) */
+int wdgh_ntk_clamp_transform(float *g, int64_t m, int64_t ldg, void *stream);
 /* in place: g <- arccos-kernel(g)/2 for n_layers==1, g/2 for n_layers==0 (hm.py:236-244,257).
  * scratch_m: float32[m]. */
 int wdgh_gntk_transform(float *g, int64_t m, int64_t ldg, int n_layers, float *scratch_m, void *stream);
@@ -226,7 +236,7 @@ int wdgh_gntk_transform(float *g, int64_t m, int64_t ldg, int n_layers, float *s
 /* One pass of the hot path from host memory: H2D copy of the CSR, labels and
  * features, plan + normaliser, Y = norm(A+I) X, the label statistics, D2H copy of
  * the counters (+ node_sum) and, if y_host != NULL, of Y.  SYNCHRONOUS.
- *   counters_host int64[WDGH_SC_HEADER + 2C + C*C], node_sum_host double[1].
+ *   counters_host int64[WDGH_SC_WORDS(C)], node_sum_host double[2].
  * Device buffers are allocated once and cached inside the library between calls. */
 int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col_host, int64_t n, int64_t nnz,
                        const float *x_host, int64_t d, const int32_t *labels_host, int32_t num_classes,

@@ -455,3 +455,98 @@ def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="k
         g_res[j], x_res[j] = acc_g, acc_x
     _, p = ttest_ind(x_res.numpy(), g_res.numpy(), axis=0, equal_var=False, nan_policy="propagate")   # :340
     return float(p / 2) if diff.mean() <= 0.5 else float(1 - p / 2)                     # :343-347
+
+
+# ---------------------------------------------------------------------------
+# utils/homophily_plot.py : the dense-adjacency variants used by synthetic_plot.py
+# (restated on the stored entries (row, col, val) of the dense matrix; cited as hp.py:LINE)
+# ---------------------------------------------------------------------------
+def plot_edge_homophily(row, col, val, label_matrix):
+    """hp.py:43-54: sum_{i!=j, a_ij>0} <l_i, l_j> / #{i!=j, a_ij>0}."""
+    row, col = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64)
+    keep = (row != col) & (np.asarray(val) > 0)
+    lab = np.asarray(label_matrix, dtype=np.float64)
+    return np.float32((lab[row[keep]] * lab[col[keep]]).sum() / keep.sum())
+
+
+def plot_node_homophily(row, col, labels, n):
+    """hp.py:81-100: like node_homophily but self-loops are NOT removed (every stored nonzero counts)."""
+    row, col = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64)
+    lab = np.asarray(labels, dtype=np.int64)
+    deg = np.bincount(row, minlength=n).astype(np.float32)
+    if row.size == 0 or int(row.max()) + 1 != n:
+        raise RuntimeError("bincount length differs from the number of nodes")
+    m = np.bincount(row[lab[row] == lab[col]], minlength=n).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        hs = m / deg
+    return np.float32(np.mean(hs[deg != 0], dtype=np.float64))
+
+
+def plot_compat_matrix(src, dst, labels):
+    """hp.py:103-125: class compatibility matrix of an edge list, self-loops INCLUDED."""
+    lab = np.asarray(labels, dtype=np.int64).reshape(-1)
+    c = int(lab.max()) + 1
+    ls, lt = lab[np.asarray(src, dtype=np.int64)], lab[np.asarray(dst, dtype=np.int64)]
+    k = (ls >= 0) & (lt >= 0)
+    h = np.bincount(ls[k] * c + lt[k], minlength=c * c).reshape(c, c).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return h / h.sum(1, keepdims=True)
+
+
+def plot_class_homophily(row, col, val, labels, n):
+    """hp.py:128-148 `our_measure(A, label)`: diagonal dropped, isolated nodes get a self-loop."""
+    row, col = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64)
+    lab = np.asarray(labels, dtype=np.int64).reshape(-1)
+    keep = (row != col) & (np.asarray(val) != 0)
+    r, q = row[keep], col[keep]
+    rs = np.bincount(r, weights=np.asarray(val, dtype=np.float64)[keep], minlength=n)
+    iso = np.nonzero(rs == 0)[0]
+    src, dst = np.concatenate([r, iso]), np.concatenate([q, iso])
+    h = plot_compat_matrix(src, dst, lab)
+    c = int(lab.max()) + 1
+    nz = lab[lab >= 0]
+    prop = np.unique(nz, return_counts=True)[1].astype(np.float32) / np.float32(nz.shape[0])
+    v = np.float32(0)
+    for k in range(c):
+        add = h[k, k] - prop[k]
+        if not np.isnan(add):
+            v = np.float32(v + max(add, 0))
+    return np.float32(v / np.float32(c - 1))
+
+
+def plot_similarity(features, row, col, val, n, label_onehot, NTK=None, hard=None, LP=1, ifsum=1, idx_train=None):
+    """hp.py:189-241: as `similarity`, optional NTK feature kernel, idx_train is an INDEX list applied after the Gram."""
+    x = torch.as_tensor(np.ascontiguousarray(features), dtype=torch.float32)
+    idx = torch.from_numpy(np.vstack([row, col]).astype(np.int64))
+    a = torch.sparse_coo_tensor(idx, torch.as_tensor(np.asarray(val, dtype=np.float32)), (n, n)).coalesce().to_dense()
+    label = torch.as_tensor(np.asarray(label_onehot), dtype=torch.float32)
+    if NTK:
+        k = torch.clamp(x @ x.T, 0, 1)
+        k = (k * (torch.pi - torch.acos(k))) / (2 * torch.pi)
+        inner = a @ k @ a.T
+    else:
+        z = a @ x
+        inner = z @ z.T
+    if idx_train is None:
+        labels = label.argmax(1)
+    else:
+        it = torch.as_tensor(np.asarray(idx_train)).long()
+        labels = label.argmax(1)[it]
+        label = label[it]
+        inner = inner[it][:, it]
+    c = int(labels.max()) + 1
+    w = torch.zeros(inner.shape[0], c)
+    for i in range(c):
+        cols = inner[:, labels == i]
+        w[:, i] = cols.sum(1) if ifsum == 1 else cols.mean(1)
+    own = w[torch.arange(labels.shape[0]), labels]
+    if hard is None:
+        nnodes, degs = (labels.shape[0], (label @ label.T).sum(1)) if ifsum == 1 else (c, 1)
+        if LP == 1:
+            ratio = (own / degs) / ((w.sum(1) - own) / (nnodes - degs))
+            ratio[torch.isnan(ratio)] = 0
+            return np.float32((ratio >= 1).float().mean().item())
+        return np.float32((((w - w * label).sum(1) <= 0) & ((w * label).sum(1) >= 0)).float().mean().item())
+    if LP == 1:
+        return np.float32(w.argmax(1).eq(labels).float().mean().item())
+    return np.float32((((w - w * label).max(1)[0] <= 0.0) & ((w * label).sum(1) >= 0)).float().mean().item())

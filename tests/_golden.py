@@ -48,3 +48,15 @@ def proj_matrix(d, seed=5):
     cols = torch.randperm(d, generator=g)[: min(24, d)].sort().values
     proj = torch.randn(d, 16, generator=g)
     return cols.numpy(), proj.double().numpy()
+
+
+def plot_flow_adjacency(z):
+    """synthetic_plot.py:94 -- normalize(adj + eye): dense row-normalised adjacency with self-loops (float32)."""
+    n = int(z["in_n"])
+    ei = z["in_edge_index"].astype(np.int64)
+    a = torch.zeros(n, n)
+    a[ei[0], ei[1]] = 1.0
+    a = a + torch.eye(n)
+    r = 1.0 / a.sum(1)
+    r[torch.isinf(r)] = 0
+    return r[:, None] * a

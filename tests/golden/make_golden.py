@@ -59,6 +59,7 @@ sys.path.insert(0, REF)
 _cwd = os.getcwd()
 os.chdir(REF)  # the reference opens "data/ind.cora.x" relative to its root
 import utils.homophily_metrics as hm  # noqa: E402
+import utils.homophily_plot as hp  # noqa: E402  (dense-adjacency variants used by synthetic_plot.py)
 import utils.util_funcs as uf  # noqa: E402
 
 
@@ -321,7 +322,52 @@ def case_edge_cases():
         save(name, **out)
 
 
+# --------------------------------------------------------------------------
+# case 4: the dense-adjacency variants of utils/homophily_plot.py through the synthetic_plot.py flow
+# --------------------------------------------------------------------------
+def case_plot_variants():
+    for nedge, h, s in ((800, 0.3, 1), (4000, 0.6, 4)):
+        base = f"{REF}/data_synthesis/{nedge}/{h}"
+        adj_raw = torch.load(f"{base}/adj_{h}_{s}.pt", weights_only=False).to_dense().clone().detach().float()
+        label = torch.load(f"{base}/label_{h}_{s}.pt", weights_only=False).to_dense().clone().detach().float()
+        labels = torch.argmax(label, 1)
+        n, c = label.shape
+        g = torch.Generator().manual_seed(300 + s)
+        centers = torch.rand(c, 24, generator=g)
+        feats_raw = (centers[labels] + 0.8 * torch.rand(n, 24, generator=g)).float()        # non-negative, like bag-of-words
+        features = torch.tensor(uf.preprocess_features(feats_raw.clone())).clone().detach()    # synthetic_plot.py:81-82
+        adj = torch.tensor(uf.normalize(adj_raw + torch.eye(n)))                              # synthetic_plot.py:94
+        raw_ei = adj_raw.to_sparse().coalesce().indices()
+        out = {"in_n": np.int64(n), "in_edge_index": t2n(raw_ei).astype(np.int32), "in_labels": t2n(labels),
+               "in_features_raw": t2n(feats_raw), "out_features": t2n(features), "out_adj_rowsum": t2n(adj.double().sum(1)),
+               "out_adj_diag": t2n(torch.diag(adj))}
+        out["out_edge_homo"] = t2n(hp.edge_homophily(adj, label))
+        out["out_node_homo"] = t2n(hp.node_homophily(adj, labels))
+        out["out_class_homo"] = t2n(hp.our_measure(adj, labels))
+        out["out_soft_las"] = t2n(hp.similarity(label, adj, label, NTK=None, hard=None, LP=1))
+        out["out_hard_las"] = t2n(hp.similarity(label, adj, label, NTK=None, hard=1, LP=1))
+        idx = torch.arange(0, n, 3)
+        out["in_idx_train"] = t2n(idx)
+        out["out_soft_las_idx"] = t2n(hp.similarity(label, adj, label, NTK=None, hard=None, LP=1, idx_train=idx))
+        out["out_soft_las_ntk"] = t2n(hp.similarity(features / features.norm(dim=1, keepdim=True), adj, label, NTK=True,
+                                                    hard=None, LP=1))
+        out["out_adj_homo"] = t2n(hp.adjusted_homo(adj, label))
+        out["out_label_info"] = t2n(hp.label_informativeness(adj, label))
+        out["out_gen_edge_homo"] = t2n(hp.generalized_edge_homophily(adj, features, label))
+        p, p_bar, pc = hp.class_distribution(adj, labels)
+        out["out_p"], out["out_p_bar"], out["out_pc"] = t2n(p), t2n(p_bar), t2n(pc)
+        ei_t = adj.nonzero()
+        out["out_compat"] = t2n(hp.compact_matrix_edge_idx(ei_t, labels))
+        for clf in ("kernel_reg0", "kernel_reg1", "gnb"):
+            seed_all(77)
+            out[f"out_kr_p_{clf}"] = np.float64(hp.classifier_based_performance_metric(
+                features, adj, labels, sample_max=300, base_classifier=clf, epochs=4))
+        out["in_kr"] = np.array([77, 300, 4], dtype=np.int64)  # seed, sample_max, epochs
+        save(f"plot_syn_{nedge}_{h}_{s}", **out)
+
+
 if __name__ == "__main__":
+    case_plot_variants()
     case_cora()
     case_synthetic()
     case_edge_cases()

@@ -164,6 +164,39 @@ def test_edge_cases(name):
         check_gram(z, ei[0], ei[1], val, n, x, labels)
 
 
+@pytest.mark.parametrize("name", G.names("plot_"))
+def test_plot_variants(name):
+    """utils/homophily_plot.py (dense-adjacency variants, synthetic_plot.py flow)."""
+    z = G.load(name)
+    n = int(z["in_n"])
+    labels = z["in_labels"]
+    a = G.plot_flow_adjacency(z)
+    close(a.double().sum(1), z["out_adj_rowsum"])
+    close(torch.diag(a), z["out_adj_diag"], rtol=1e-6)
+    sp_ = a.to_sparse().coalesce()
+    row, col, val = sp_.indices()[0].numpy(), sp_.indices()[1].numpy(), sp_.values().numpy()
+    c = int(labels.max()) + 1
+    oh = np.eye(c, dtype=np.float32)[labels]
+    x = z["out_features"]
+    close(O.plot_edge_homophily(row, col, val, oh), z["out_edge_homo"])
+    close(O.plot_node_homophily(row, col, labels, n), z["out_node_homo"])
+    close(O.plot_class_homophily(row, col, val, labels, n), z["out_class_homo"])
+    nzr, nzc = a.nonzero().T.numpy()
+    close(O.plot_compat_matrix(nzr, nzc, labels), z["out_compat"])
+    close(O.plot_similarity(oh, row, col, val, n, oh), z["out_soft_las"], rtol=0, atol=1e-6)
+    close(O.plot_similarity(oh, row, col, val, n, oh, hard=1), z["out_hard_las"], rtol=0, atol=1e-6)
+    close(O.plot_similarity(oh, row, col, val, n, oh, idx_train=z["in_idx_train"]), z["out_soft_las_idx"], rtol=0, atol=1e-6)
+    xn = x / np.linalg.norm(x, axis=1, keepdims=True)
+    close(O.plot_similarity(xn, row, col, val, n, oh, NTK=True), z["out_soft_las_ntk"], rtol=0, atol=1e-6)
+    p, p_bar, pc = O.class_distribution(row, col, labels, n)
+    close(p, z["out_p"]); close(p_bar, z["out_p_bar"]); close(pc, z["out_pc"])
+    s2 = np.float32(np.sum(p_bar.astype(np.float32) ** 2, dtype=np.float32))
+    close((O.plot_edge_homophily(row, col, val, oh) - s2) / (1 - s2), z["out_adj_homo"], rtol=1e-4)
+    close(O.label_informativeness(row, col, labels, n), z["out_label_info"], rtol=1e-4, atol=1e-5)
+    close(O.generalized_edge_homophily(row, col, x, n), z["out_gen_edge_homo"], rtol=1e-4)
+    close(O.normalize_tensor(z["in_features_raw"]).numpy(), x, rtol=1e-6)   # preprocess_features == row normalisation
+
+
 def test_coalesce_and_counts_small():
     # duplicates are summed, order is row-major (torch .coalesce())
     row = np.array([2, 0, 2, 1, 0]); col = np.array([1, 2, 1, 1, 0]); val = np.array([1, 2, 3, 4, 5], np.float32)

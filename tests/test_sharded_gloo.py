@@ -67,7 +67,7 @@ def _worker(rank, world, port, out):
                 np.add.at(y, lrow - r0, (dv[lcol][:, None] * xf[lcol]))
                 y = (y + dv[r0:r1, None] * xf[r0:r1]) * dv[r0:r1, None]
                 s = O.structure_counts(lrow, lcol, lab, n, num_classes=C)
-                cnt = np.zeros(_lib.SC_HEADER + 2 * C + C * C, np.int64)
+                cnt = np.zeros(_lib.sc_words(C), np.int64)
                 cnt[_lib.SC_MATCH_ALL], cnt[_lib.SC_MATCH_LAB] = s["match_all"], s["match_lab"]
                 cnt[_lib.SC_N_LAB], cnt[_lib.SC_N_SELF] = s["n_lab"], s["n_selfloop"]
                 d_loc, m_loc = s["deg_nsl"][r0:r1], s["match_nsl"][r0:r1]
@@ -79,13 +79,13 @@ def _worker(rank, world, port, out):
                 cnt[_lib.SC_HEADER:_lib.SC_HEADER + C] = np.bincount(ll[ll >= 0], minlength=C)
                 cnt[_lib.SC_HEADER + C:_lib.SC_HEADER + 2 * C] = np.bincount(ll[ll >= 0], weights=np.diff(lrp)[ll >= 0],
                                                                             minlength=C)
-                cnt[_lib.SC_HEADER + 2 * C:] = s["hist"].ravel()
+                cnt[_lib.SC_HEADER + 2 * C:_lib.SC_HEADER + 2 * C + C * C] = s["hist"].ravel()
                 node_sum = (m_loc[nz].astype(np.float32) / d_loc[nz].astype(np.float32)).astype(np.float64).sum()
-                return torch.from_numpy(y), torch.from_numpy(cnt), torch.tensor([node_sum], dtype=torch.float64)
+                return torch.from_numpy(y), torch.from_numpy(cnt), torch.tensor([node_sum, 0.0], dtype=torch.float64)
 
         pipe = OracleShard(part, rank, torch.from_numpy(x[r0:r1]), torch.from_numpy(labels[r0:r1].astype(np.int32)), C)
         y, cnt, node_sum = pipe.step(_lib.NORM_SYM, True)
-        out.put((rank, r0, r1, y.numpy(), cnt.numpy(), float(node_sum)))
+        out.put((rank, r0, r1, y.numpy(), cnt.numpy(), float(node_sum[0])))
     finally:
         dist.destroy_process_group()
 
@@ -140,7 +140,7 @@ def test_world2_step_matches_single_process_oracle():
     for r in res:  # identical all-reduced counters on both ranks
         cnt = r[4]
         assert cnt[_lib.SC_MATCH_ALL] == s["match_all"] and cnt[_lib.SC_N_LAB] == s["n_lab"]
-        assert np.array_equal(cnt[_lib.SC_HEADER + 2 * C:].reshape(C, C), s["hist"])
+        assert np.array_equal(cnt[_lib.SC_HEADER + 2 * C:_lib.SC_HEADER + 2 * C + C * C].reshape(C, C), s["hist"])
         assert np.array_equal(cnt[_lib.SC_HEADER:_lib.SC_HEADER + C], s["class_count"])
         assert cnt[_lib.SC_NBINS] == np.nonzero(s["deg_nsl"])[0].max() + 1
         assert cnt[_lib.SC_N_NODES_NSL] == int((s["deg_nsl"] > 0).sum())

@@ -212,6 +212,18 @@ __global__ void gntk_apply_kernel(float *__restrict__ g, int64_t m, int64_t ldg,
   }
 }
 
+// NTK branch of homophily_plot.py similarity (:191-193): k = clamp(g,0,1); g = k (pi - acos k) / (2 pi)
+__global__ void ntk_clamp_kernel(float *__restrict__ g, int64_t m, int64_t ldg) {
+  const float pi = 3.14159265358979323846f;
+  const int64_t total = m * m;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / m, j = t - i * m;
+    const float k = fminf(fmaxf(g[i * ldg + j], 0.f), 1.f);
+    g[i * ldg + j] = (k * (pi - acosf(k))) / (2.f * pi);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // per-entry feature cosine (hm.py:167-172 / 181-186): one warp per entry
 // ---------------------------------------------------------------------------
@@ -239,7 +251,8 @@ edge_cosine_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
     const int64_t e = ids ? ids[t] : t;
     const int64_t i = row_of_entry(rowptr, n, e);
     const int64_t j = col[e];
-    if (mode == 0) {
+    const bool raw_dot = (mode & 2) != 0;
+    if ((mode & 1) == 0) {
       if (i == j) continue;                       // adj - diag(adj)   (hm.py:170)
       if (val != nullptr && !(val[e] > 0.f)) continue;  // (adj > 0)      (hm.py:171)
     }
@@ -254,7 +267,7 @@ edge_cosine_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
     dot = warp_sum(dot);
     na = warp_sum(na);
     nb = warp_sum(nb);
-    float sim = dot / (sqrtf(na) * sqrtf(nb));
+    float sim = raw_dot ? dot : dot / (sqrtf(na) * sqrtf(nb));
     if (isnan(sim)) sim = 0.f;
     sum += (double)sim;
     cnt += 1;
@@ -331,12 +344,20 @@ extern "C" int wdgh_gntk_transform(float *g, int64_t m, int64_t ldg, int n_layer
   return 0;
 }
 
+extern "C" int wdgh_ntk_clamp_transform(float *g, int64_t m, int64_t ldg, void *stream) {
+  WDGH_REQUIRE(g && m >= 0 && ldg >= m, "wdgh_ntk_clamp_transform: bad arguments");
+  if (m == 0) return 0;
+  ntk_clamp_kernel<<<persistent_grid(ceil_div(m * m, 256), 8), 256, 0, as_stream(stream)>>>(g, m, ldg);
+  WDGH_LAUNCHED("ntk_clamp_kernel");
+  return 0;
+}
+
 extern "C" int wdgh_edge_cosine(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                                 const float *x, int64_t d, int64_t ldx, int mode, const int64_t *entry_ids,
                                 int64_t n_ids, double *out_sum, unsigned long long *out_cnt, void *stream) {
   WDGH_REQUIRE(rowptr && x && out_sum && out_cnt && n >= 0 && d >= 1 && ldx >= d && n_ids >= 0,
                "wdgh_edge_cosine: bad arguments");
-  WDGH_REQUIRE(mode == 0 || (mode == 1 && entry_ids != nullptr), "wdgh_edge_cosine: bad mode");
+  WDGH_REQUIRE(mode >= 0 && mode <= 3 && ((mode & 1) == 0 || entry_ids != nullptr), "wdgh_edge_cosine: bad mode");
   cudaStream_t st = as_stream(stream);
   WDGH_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
   WDGH_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(unsigned long long), st));

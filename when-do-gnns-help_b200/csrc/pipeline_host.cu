@@ -48,7 +48,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   WDGH_REQUIRE(n > 0 && nnz >= 0 && d > 0 && num_classes >= 1 && (col_host || nnz == 0), "wdgh_pipeline_host: bad shape");
   HostPipelineCache &c = g_cache;
   const int C = num_classes;
-  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  const size_t n_counters = WDGH_SC_WORDS((size_t)C);
   const int64_t cap = 2 * nnz / kHostPipelineThreshold + 2;
   if (c.n != n || c.nnz != nnz || c.d != d || c.C != C) {
     c.release();
@@ -65,7 +65,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMalloc(&c.match, n * sizeof(int32_t)));
     WDGH_CUDA(cudaMalloc(&c.plan, WDGH_PLAN_WORDS(cap, nnz) * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.counters, n_counters * sizeof(int64_t)));
-    WDGH_CUDA(cudaMalloc(&c.node_sum, sizeof(double)));
+    WDGH_CUDA(cudaMalloc(&c.node_sum, 2 * sizeof(double)));
     c.n = n; c.nnz = nnz; c.d = d; c.C = C; c.cap = cap;
   }
   cudaStream_t st = c.st;
@@ -94,7 +94,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
                                  c.partial, c.counters, c.node_sum, c.deg, c.match, c.labels8, n, 0, 0, st);
   if (rc) return rc;
   WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+  WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (y_host) WDGH_CUDA(cudaMemcpyAsync(y_host, c.y, n * d * sizeof(float), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaStreamSynchronize(st));
   return 0;

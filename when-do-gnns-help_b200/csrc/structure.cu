@@ -19,7 +19,7 @@ struct EdgeAcc {
 };
 
 __device__ __forceinline__ void visit(int64_t row, int li, int j, int lj, int C, EdgeAcc &a, int &m_nsl, int &d_nsl,
-                                      int &key) {
+                                      int &key, bool hist_self = false) {
   const bool self = (j == row);
   const bool same = (li == lj);
   const bool both = (li >= 0) && (lj >= 0);
@@ -31,6 +31,8 @@ __device__ __forceinline__ void visit(int64_t row, int li, int j, int lj, int C,
     d_nsl += 1;
     m_nsl += same;
     if (both) key = li * C + lj;
+  } else if (hist_self && both) {
+    key = li * C + lj;
   }
 }
 
@@ -208,7 +210,7 @@ structure_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
 __global__ void __launch_bounds__(256)
 structure_coo_kernel(const int64_t *__restrict__ edge_index, int64_t E, int64_t n,
                      const int32_t *__restrict__ labels, int C, unsigned long long *__restrict__ counters,
-                     int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl) {
+                     int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl, bool hist_self) {
   extern __shared__ unsigned s_hist[];
   const bool use_smem = (C * C <= kHistSmemBins);
   unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
@@ -226,7 +228,7 @@ structure_coo_kernel(const int64_t *__restrict__ edge_index, int64_t E, int64_t 
       const int64_t src = edge_index[t], dst = edge_index[E + t];
       const int li = __ldg(labels + src), lj = __ldg(labels + dst);
       int m = 0, d = 0;
-      visit(src, li, (int)dst, lj, C, acc, m, d, key);
+      visit(src, li, (int)dst, lj, C, acc, m, d, key, hist_self);
       if (d) atomicAdd(&deg_nsl[src], 1);
       if (m) atomicAdd(&match_nsl[src], 1);
     }
@@ -256,8 +258,9 @@ structure_nodes_kernel(const int64_t *__restrict__ rowptr, int64_t n, const int3
     __syncthreads();
   }
   unsigned long long *cls = use_smem ? s_cls : g_cls;
-  double sum = 0.0;
+  double sum = 0.0, sum_self = 0.0;
   long long n_nsl = 0, n_empty = 0, nbins = 0;
+  unsigned long long *g_iso = counters + WDGH_SC_HEADER + 2 * C + (size_t)C * C;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int d = deg_nsl[i], m = match_nsl[i];
@@ -268,19 +271,26 @@ structure_nodes_kernel(const int64_t *__restrict__ rowptr, int64_t n, const int3
       nbins = i + row_offset + 1;  // i is increasing per thread
     }
     if (deg_all == 0) n_empty += 1;
+    if (rowptr && deg_all > 0) {  // diagonal entries kept and counted as matches (homophily_plot.py:92-100)
+      const int64_t self = deg_all - d;
+      sum_self += (double)((float)(m + self) / (float)deg_all);
+    }
     const int l = labels[i + row_offset];
+    if (l >= 0 && l < C && d == 0) atomicAdd(&g_iso[l], 1ull);  // rare: isolated nodes only
     if (l >= 0 && l < C) {
       atomicAdd(&cls[l], 1ull);
       if (rowptr) atomicAdd(&cls[C + l], (unsigned long long)deg_all);
     }
   }
   sum = warp_sum(sum);
+  sum_self = warp_sum(sum_self);
   n_nsl = warp_sum(n_nsl);
   n_empty = warp_sum(n_empty);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nbins = max(nbins, __shfl_xor_sync(0xffffffffu, nbins, o));
   if ((threadIdx.x & 31) == 0) {
     if (sum != 0.0) atomicAdd(node_sum, sum);
+    if (sum_self != 0.0) atomicAdd(node_sum + 1, sum_self);
     if (n_nsl) atomicAdd(&counters[WDGH_SC_N_NODES_NSL], (unsigned long long)n_nsl);
     if (n_empty) atomicAdd(&counters[WDGH_SC_N_EMPTY], (unsigned long long)n_empty);
     if (nbins) atomicMax(&counters[WDGH_SC_NBINS], (unsigned long long)nbins);
@@ -343,9 +353,9 @@ using namespace wdgh;
 
 int wdgh::structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint8_t *labels_u8_scratch,
                             int64_t *counters, double *node_sum, const uint8_t **labels8_out, cudaStream_t st) {
-  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  const size_t n_counters = WDGH_SC_WORDS((size_t)C);
   WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
-  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
+  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, 2 * sizeof(double), st));
   *labels8_out = nullptr;
   if (labels_u8_scratch != nullptr && C <= 254 && n_labels > 0) {
     labels_to_u8_kernel<<<persistent_grid(ceil_div(n_labels, 256), 8), 256, 0, st>>>(
@@ -407,16 +417,17 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
 
 extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,
                                          const int32_t *labels, int32_t num_classes, int64_t *counters,
-                                         double *node_sum, int32_t *deg_nsl, int32_t *match_nsl, void *stream) {
+                                         double *node_sum, int32_t *deg_nsl, int32_t *match_nsl,
+                                         int hist_includes_self_loops, void *stream) {
   WDGH_REQUIRE(labels && counters && node_sum && deg_nsl && match_nsl && (edge_index || num_edges == 0),
                "wdgh_structure_counts_coo: null pointer");
   WDGH_REQUIRE(n >= 0 && num_edges >= 0 && num_classes >= 1 && num_classes <= 46340,
                "wdgh_structure_counts_coo: bad shape");
   cudaStream_t st = as_stream(stream);
   const int C = num_classes;
-  const size_t n_counters = WDGH_SC_HEADER + 2 * (size_t)C + (size_t)C * C;
+  const size_t n_counters = WDGH_SC_WORDS((size_t)C);
   WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
-  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, sizeof(double), st));
+  WDGH_CUDA(cudaMemsetAsync(node_sum, 0, 2 * sizeof(double), st));
   if (n == 0) return 0;
   WDGH_CUDA(cudaMemsetAsync(deg_nsl, 0, n * sizeof(int32_t), st));
   WDGH_CUDA(cudaMemsetAsync(match_nsl, 0, n * sizeof(int32_t), st));
@@ -424,7 +435,7 @@ extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_
   const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
   if (num_edges > 0) {
     structure_coo_kernel<<<persistent_grid(ceil_div(num_edges, 256), 8), 256, hist_smem, st>>>(
-        edge_index, num_edges, n, labels, C, cnt, deg_nsl, match_nsl);
+        edge_index, num_edges, n, labels, C, cnt, deg_nsl, match_nsl, hist_includes_self_loops != 0);
     WDGH_LAUNCHED("structure_coo_kernel");
   }
   const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;

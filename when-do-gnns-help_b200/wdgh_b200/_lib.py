@@ -17,6 +17,11 @@ UNIT = 1024
 SC_MATCH_ALL, SC_MATCH_LAB, SC_N_LAB, SC_N_SELF, SC_N_EMPTY, SC_NBINS, SC_N_NODES_NSL, SC_N_MULTI_NEG = range(8)
 SC_HEADER = 8
 
+
+def sc_words(c: int) -> int:
+    """Length of the counters array for c classes (WDGH_SC_WORDS)."""
+    return SC_HEADER + 3 * c + c * c
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python when-do-gnns-help_b200/build.py` "
@@ -46,7 +51,7 @@ SIGNATURES = {
     "wdgh_structure_counts": [_p, _p, _i64, _i64, _p, _i32, _p, C.POINTER(_i64), _p, _p, _p, _p, _p, _i64, _i64, _p],
     "wdgh_spmm_structure_fused": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _i32, _p,
                                   C.POINTER(_i64), _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p],
-    "wdgh_structure_counts_coo": [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p],
+    "wdgh_structure_counts_coo": [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _int, _p],
     "wdgh_edge_label_rows_equal": [_p, _p, _i64, _p, _i64, _i64, _p, _p],
     "wdgh_edge_cosine": [_p, _p, _p, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p],
     "wdgh_gram_workspace_floats": [_i64, _i64],
@@ -54,6 +59,7 @@ SIGNATURES = {
     "wdgh_gather_rows": [_p, _i64, _i64, _p, _i64, _p, _i64, _p],
     "wdgh_class_colsum": [_p, _i64, _i64, _p, _i32, _int, _p, _p],
     "wdgh_las_score": [_p, _p, _p, _i64, _i32, _int, _int, _int, _p, _p, _p],
+    "wdgh_ntk_clamp_transform": [_p, _i64, _i64, _p],
     "wdgh_gntk_transform": [_p, _i64, _i64, _int, _p, _p],
     "wdgh_pipeline_host": [_p, _p, _i64, _i64, _p, _i64, _p, _i32, _int, _int, _p, _p, _p],
     "wdgh_pipeline_host_release": [],

@@ -225,7 +225,9 @@ class StructureCounts:
     class_count: np.ndarray   # [C] int64
     class_deg: np.ndarray     # [C] int64, sum of stored entries per row over the class
     hist: np.ndarray          # [C, C] int64
-    node_sum: float           # sum_i f32(match_i)/f32(deg_i)
+    node_sum: float           # sum_i f32(match_i)/f32(deg_i), diagonal excluded
+    node_sum_self: float      # same with stored diagonal entries kept and counted as matches
+    class_isolated: np.ndarray  # [C] int64, class-c nodes without an off-diagonal entry
     deg_nsl: torch.Tensor     # [n] int32 (device)
     match_nsl: torch.Tensor   # [n] int32 (device)
 
@@ -252,7 +254,8 @@ def _unpack_counts(n, nnz, c, counters, node_sum, deg, match):
         n_nodes_nsl=int(h[_lib.SC_N_NODES_NSL]),
         class_count=h[H:H + c].copy(), class_deg=h[H + c:H + 2 * c].copy(),
         hist=h[H + 2 * c:H + 2 * c + c * c].reshape(c, c).copy(),
-        node_sum=float(node_sum.item()), deg_nsl=deg, match_nsl=match)
+        node_sum=float(node_sum[0].item()), node_sum_self=float(node_sum[1].item()),
+        class_isolated=h[H + 2 * c + c * c:H + 3 * c + c * c].copy(), deg_nsl=deg, match_nsl=match)
 
 
 def structure_counts_raw(g: CSRGraph, labels32, num_classes, scratch=None):
@@ -265,8 +268,8 @@ def structure_counts_raw(g: CSRGraph, labels32, num_classes, scratch=None):
     if n_labels < g.row_offset + g.n:
         raise ValueError("labels must cover every (global) node id of the shard")
     if scratch is None:
-        scratch = (torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev),
-                   torch.empty(1, dtype=torch.float64, device=dev),
+        scratch = (torch.empty(_lib.sc_words(c), dtype=torch.int64, device=dev),
+                   torch.empty(2, dtype=torch.float64, device=dev),
                    torch.empty(g.n, dtype=torch.int32, device=dev),
                    torch.empty(g.n, dtype=torch.int32, device=dev),
                    torch.empty(n_labels, dtype=torch.uint8, device=dev))
@@ -304,8 +307,8 @@ def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, a
     y = out if out is not None else torch.empty((g.n, d), dtype=torch.float32, device=dev)
     n_labels = int(labels32.shape[0])
     if scratch is None:
-        scratch = (torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev),
-                   torch.empty(1, dtype=torch.float64, device=dev),
+        scratch = (torch.empty(_lib.sc_words(c), dtype=torch.int64, device=dev),
+                   torch.empty(2, dtype=torch.float64, device=dev),
                    torch.empty(g.n, dtype=torch.int32, device=dev),
                    torch.empty(g.n, dtype=torch.int32, device=dev),
                    torch.empty(n_labels, dtype=torch.uint8, device=dev))
@@ -327,17 +330,18 @@ def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, a
     return y, scratch
 
 
-def structure_counts_coo(edge_index, n, labels32, num_classes) -> StructureCounts:
+def structure_counts_coo(edge_index, n, labels32, num_classes, hist_includes_self_loops=False) -> StructureCounts:
     ei = _cuda(edge_index, torch.int64)
     c = int(num_classes)
     e = int(ei.shape[1])
     dev = ei.device
-    counters = torch.empty(_lib.SC_HEADER + 2 * c + c * c, dtype=torch.int64, device=dev)
-    node_sum = torch.empty(1, dtype=torch.float64, device=dev)
+    counters = torch.empty(_lib.sc_words(c), dtype=torch.int64, device=dev)
+    node_sum = torch.empty(2, dtype=torch.float64, device=dev)
     deg = torch.empty(n, dtype=torch.int32, device=dev)
     match = torch.empty(n, dtype=torch.int32, device=dev)
     check(lib.wdgh_structure_counts_coo(ptr(ei), e, n, ptr(labels32), c, ptr(counters), ptr(node_sum), ptr(deg),
-                                        ptr(match), stream_ptr()), "wdgh_structure_counts_coo")
+                                        ptr(match), int(bool(hist_includes_self_loops)), stream_ptr()),
+          "wdgh_structure_counts_coo")
     return _unpack_counts(n, e, c, counters, node_sum, deg, match)
 
 
@@ -349,8 +353,9 @@ def edge_label_rows_equal(g: CSRGraph, label_rows) -> int:
     return int(out.item())
 
 
-def edge_cosine(g: CSRGraph, x, entry_ids=None):
-    """(sum of cosines, entries counted): all off-diagonal positive entries, or the listed entry ids."""
+def edge_cosine(g: CSRGraph, x, entry_ids=None, raw_dot=False):
+    """(sum of cosines -- or plain dot products --, entries counted): all off-diagonal positive entries,
+    or the listed entry ids."""
     x = _cuda(x, torch.float32)
     s = torch.empty(1, dtype=torch.float64, device=g.device)
     cnt = torch.empty(1, dtype=torch.int64, device=g.device)
@@ -359,6 +364,7 @@ def edge_cosine(g: CSRGraph, x, entry_ids=None):
     else:
         ids = _cuda(entry_ids, torch.int64)
         mode, n_ids = 1, int(ids.shape[0])
+    mode |= 2 if raw_dot else 0
     check(lib.wdgh_edge_cosine(ptr(g.rowptr), ptr(g.col), ptr(g.val), g.n, ptr(x), x.shape[1], x.stride(0), mode,
                                ptr(ids), n_ids, ptr(s), ptr(cnt), stream_ptr()), "wdgh_edge_cosine")
     return float(s.item()), int(cnt.item())
@@ -420,6 +426,11 @@ def gntk_transform_(gm, n_layers):
     scratch = torch.empty(m, dtype=torch.float32, device=gm.device)
     check(lib.wdgh_gntk_transform(ptr(gm), m, gm.stride(0), int(n_layers), ptr(scratch), stream_ptr()),
           "wdgh_gntk_transform")
+    return gm
+
+
+def ntk_clamp_transform_(gm):
+    check(lib.wdgh_ntk_clamp_transform(ptr(gm), int(gm.shape[0]), gm.stride(0), stream_ptr()), "wdgh_ntk_clamp_transform")
     return gm
 
 
