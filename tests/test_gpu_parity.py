@@ -522,3 +522,23 @@ def test_plot_variants_golden(W, name):
             close(p_val, z[f"out_kr_p_{clf}"], rtol=5e-2, atol=1e-9)
     with pytest.raises(AttributeError):   # the reference trips over `sample.device` when it does not subsample
         hp.classifier_based_performance_metric(feats, adj, labels, 10 * n, base_classifier="kernel_reg0", epochs=1)
+
+
+def test_raw_abi_example(W):
+    """The ctypes-only snippet of INTEGRATION.md section 2 (tools/abi_example.py) against the oracle."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "abi_example.py")
+    spec = importlib.util.spec_from_file_location("abi_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n, d = 4000, 128
+    row, col, _ = powerlaw_graph(n, 9, seed=11)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    x = np.random.default_rng(2).standard_normal((n, d)).astype(np.float32)
+    A = sparse(row, col, np.ones(row.shape[0], np.float32), n)
+    y = mod.sgc1_propagate(A, torch.from_numpy(x).cuda()).cpu().numpy()
+    r2, c2, v2 = O.sys_normalized_adjacency(row, col, np.ones(row.shape[0], np.float32), n)
+    ref = O.spmm(r2, c2, v2, n, x)
+    np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * np.abs(ref).max())
