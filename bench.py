@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--homophily", type=float, default=0.3)
     ap.add_argument("--cpu-sample-nodes", type=int, default=1_000_000)
     ap.add_argument("--slabs", type=int, default=0, help="feature column slabs for the N>1 pipeline (0 = default)")
+    ap.add_argument("--no-phased", action="store_true", help="N>1: plain all-gather then aggregate (no overlap)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -254,7 +255,8 @@ def main():
                                                    deg_code=code, scratch=scratch[0])
             return scratch[0][0], scratch[0][1]
     else:
-        pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C, slabs=(args.slabs or None))
+        pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C, slabs=(args.slabs or None),
+                                phased=(False if args.no_phased else None))
 
         def step():
             _, counters, node_sum = pipe.step(W.NORM_SYM, True)
@@ -403,13 +405,20 @@ def run_e2e(args, W, G, world, rank, device, g, x_local, labels_local, nnz, part
     else:
         from wdgh_b200.sharded import CudaShardedStats
 
+        # persistent device buffers; every step refills them from pinned host memory, rebuilds the plan /
+        # degree scales / column segments and runs the sharded step (peer mappings are set up once)
+        gg = G.CSRGraph(torch.empty_like(g.rowptr), torch.empty_like(g.col), None, rows, row_offset=g.row_offset,
+                        n_global=n)
+        x_dev = torch.empty_like(x_local)
+        lab_dev = torch.empty_like(labels_local)
+        pipe = CudaShardedStats(gg, part, rank, x_dev, lab_dev, C, phased=(False if args.no_phased else None))
+
         def once():
-            rp = rowptr_h.to(device, non_blocking=True)
-            cl = col_h.to(device, non_blocking=True)
-            xx = x_h.to(device, non_blocking=True)
-            lb = lab_h.to(device, non_blocking=True)
-            gg = G.CSRGraph(rp, cl, None, rows, row_offset=g.row_offset, n_global=n)
-            pipe = CudaShardedStats(gg, part, rank, xx, lb, C)
+            gg.rowptr.copy_(rowptr_h, non_blocking=True)
+            gg.col.copy_(col_h, non_blocking=True)
+            pipe.x_local[:rows].copy_(x_h, non_blocking=True)
+            pipe.labels_local[:rows].copy_(lab_h, non_blocking=True)
+            pipe.reset_graph()
             _, counters, node_sum = pipe.step(W.NORM_SYM, True)
             return counters.cpu(), node_sum.cpu()
         once()

@@ -125,6 +125,26 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
                   const int64_t *plan_i64, const int64_t *plan_host, float *partial,
                   int64_t row_offset, void *stream);
 
+/* ---- phased aggregation (overlap of the feature all-gather with compute, N > 1) ---- */
+/* seg[b][r] (int64[num_bounds][n]) = first stored entry of row r whose column id is >= bounds_dev[b]; with
+ * bounds = the partition's node-id boundaries, [seg[b][r], seg[b+1][r]) are the entries of row r whose source
+ * node lives on rank b (columns are sorted inside a row). */
+int wdgh_column_segments(const int64_t *rowptr, const int32_t *col, int64_t n,
+                         const int64_t *bounds_dev, int32_t num_bounds, int64_t *seg, void *stream);
+/* flags[r] = 1 for the rows the plan splits into chunks (uint8[n]) */
+int wdgh_plan_heavy_flags(const int64_t *plan_i64, const int64_t *plan_host, int64_t n, uint8_t *flags, void *stream);
+/* wdgh_spmm_csr restricted to the entries [range_begin[r], range_end[r]) of every row r:
+ *   accumulate != 0 : y += (instead of y =);   finalize != 0 : apply the self loop and the row scale now
+ *   (earlier phases store raw partial sums);   run_split_rows != 0 : afterwards compute the split rows over their
+ *   full column range (they need all of x).  Needs 16-byte aligned rows and d in {32, 64} or d >= 128. */
+int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, const int64_t *range_end,
+                         const int32_t *col, const float *val, int64_t n,
+                         const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
+                         int norm, int add_self_loop, const float *dinv, const uint8_t *deg_code,
+                         const uint8_t *skip_rows, int accumulate, int finalize, int run_split_rows,
+                         const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                         int64_t row_offset, void *stream);
+
 /* ---- label metrics: one pass over the edges ------------------------------ */
 /* Integer statistics every label metric of homophily_metrics.py is a ratio of
  * (edge / node / class / adjusted homophily, label informativeness; hm.py:43-161).

@@ -32,6 +32,7 @@ struct Vec<4> {
   float4 v;
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load(const float *p) { v = ldg_na(reinterpret_cast<const float4 *>(p)); }
+  __device__ __forceinline__ void load_plain(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
   __device__ __forceinline__ void fma(float w, const Vec &o) {
     v.x = fmaf(w, o.v.x, v.x);
     v.y = fmaf(w, o.v.y, v.y);
@@ -52,6 +53,7 @@ struct Vec<2> {
   __device__ __forceinline__ void load(const float *p) {
     asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   }
+  __device__ __forceinline__ void load_plain(const float *p) { v = *reinterpret_cast<const float2 *>(p); }
   __device__ __forceinline__ void fma(float w, const Vec &o) {
     v.x = fmaf(w, o.v.x, v.x);
     v.y = fmaf(w, o.v.y, v.y);
@@ -68,6 +70,7 @@ struct Vec<1> {
   float v;
   __device__ __forceinline__ void zero() { v = 0.f; }
   __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
+  __device__ __forceinline__ void load_plain(const float *p) { v = *p; }
   __device__ __forceinline__ void fma(float w, const Vec &o) { v = fmaf(w, o.v, v); }
   __device__ __forceinline__ void add(const Vec &o) { v += o.v; }
   __device__ __forceinline__ void scale(float s) { v *= s; }
@@ -240,13 +243,23 @@ struct StatsArgs {
   int32_t *deg_nsl, *match_nsl;  // per local row
 };
 
+// Ranged / phased aggregation: the kernel normally walks CSR rows [rowptr[r], rowptr[r+1]); with row_end set it
+// walks [rowptr[r], row_end[r]) instead (a column range of every row, e.g. the entries whose source node lives on
+// one rank), optionally adding to what Y already holds and deferring the self-loop + D^-1/2 scaling to the last phase.
+struct RangeArgs {
+  const int64_t *row_end;  // nullptr: plain CSR
+  const uint8_t *skip;     // nullptr, or 1 for rows that are handled elsewhere (split rows)
+  int accumulate;          // y += partial instead of y = partial
+  int finalize;            // apply self loop and row scale (0: store the raw partial sum)
+};
+
 template <int VEC, int NCH, bool HAS_VAL, bool FULL, int MINB, bool STATS>
 __global__ void __launch_bounds__(32, MINB)
 spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                            const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
                            float *__restrict__ y, int64_t ldy, int norm, int self_loop,
                            const float *__restrict__ dinv, const uint8_t *__restrict__ deg_code, int64_t threshold,
-                           int64_t row_offset, StatsArgs sa) {
+                           int64_t row_offset, StatsArgs sa, RangeArgs ra) {
   extern __shared__ unsigned s_stats[];  // STATS: [C*C] class-pair histogram, then 4 scalar counters
   unsigned *s_cnt = s_stats + (STATS ? sa.C * sa.C : 0);
   if (STATS) {
@@ -285,7 +298,8 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     e = 0;
     if (r < n) {
       s = __ldg(rowptr + r);
-      e = __ldg(rowptr + r + 1);
+      e = ra.row_end ? __ldg(ra.row_end + r) : __ldg(rowptr + r + 1);
+      if (ra.skip && __ldg(ra.skip + r)) e = s + threshold + 1;  // marks the row as split ("heavy")
     }
   };
   // column ids + weights of the segment [pos, pos+32) of row `r`.  With STATS the label bytes of the row
@@ -419,19 +433,28 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
     if (!next_issued) load_seg(s1, e1, r1, nj, nw, nlir, nljr);
     if (!heavy) {
       const int64_t grow = row + row_offset;
-      const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
+      const float si = (norm != WDGH_NORM_NONE && ra.finalize) ? __ldg(dinv + grow) : 1.f;
       const float self_w = sym ? si : 1.f;
 #pragma unroll
       for (int t = 0; t < NCH; ++t) {
         if (live[t]) {
           const int c = cbase + (t * 32 + lane) * VEC;
-          if (self_loop) {
-            Vec<VEC> xi;
-            xi.load(x + grow * ldx + c);
-            acc[t].fma(self_w, xi);
+          if (ra.accumulate) {  // partial sum of the earlier phases (plain load: written by a previous launch)
+            Vec<VEC> prev;
+            prev.load_plain(y + row * ldy + c);
+            acc[t].add(prev);
           }
-          acc[t].scale(si);
-          acc[t].store_stream(y + row * ldy + c);
+          if (ra.finalize) {
+            if (self_loop) {
+              Vec<VEC> xi;
+              xi.load(x + grow * ldx + c);
+              acc[t].fma(self_w, xi);
+            }
+            acc[t].scale(si);
+            acc[t].store_stream(y + row * ldy + c);
+          } else {
+            acc[t].store(y + row * ldy + c);  // re-read by the next phase: keep it cacheable
+          }
         }
       }
     }
@@ -671,6 +694,8 @@ struct SpmmArgs {
   int64_t threshold, n_heavy, n_chunks, row_offset, nnz, n_units;
   bool stats = false;
   StatsArgs sa = {nullptr, 0, nullptr, nullptr, nullptr};
+  RangeArgs ra = {nullptr, nullptr, 0, 1};
+  bool heavy_pass = true;  // run the split-row chunk kernels
   float *partial;
   int64_t ldp;
   cudaStream_t st;
@@ -771,12 +796,12 @@ static int launch_pipelined(const SpmmArgs &a) {
 #define WDGH_PIPE_LAUNCH(FULLV, MINB)                                                                              \
   spmm_rows_pipelined_kernel<VEC, NCH, HAS_VAL, FULLV, MINB, false><<<grid, 32, 0, a.st>>>(                           \
       a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
-      a.row_offset, a.sa)
+      a.row_offset, a.sa, a.ra)
 #define WDGH_PIPE_LAUNCH_STATS(FULLV, MINB)                                                                        \
   spmm_rows_pipelined_kernel<4, NCH, false, FULLV, MINB, true>                                                        \
       <<<grid, 32, (a.sa.C * a.sa.C + 4) * sizeof(unsigned), a.st>>>(a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, \
                                                                       a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, \
-                                                                      a.threshold, a.row_offset, a.sa)
+                                                                      a.threshold, a.row_offset, a.sa, a.ra)
   if (a.stats && VEC == 4) {  // binary adjacency only (checked by the caller)
     if (full && NCH == 1) WDGH_PIPE_LAUNCH_STATS(true, 32);
     else if (full) WDGH_PIPE_LAUNCH_STATS(true, 16);
@@ -806,7 +831,7 @@ static int dispatch(const SpmmArgs &a, bool vec4) {
     else if (d <= 128) rc = launch_pipelined<4, 1, HAS_VAL>(a);
     else if (d <= 256) rc = launch_pipelined<4, 2, HAS_VAL>(a);
     else rc = launch_pipelined<4, 4, HAS_VAL>(a);
-    if (rc) return rc;
+    if (rc || !a.heavy_pass) return rc;
     if (d <= 128) return launch_heavy<4, 1, HAS_VAL>(a);
     if (d <= 256) return launch_heavy<4, 2, HAS_VAL>(a);
     return launch_heavy<4, 4, HAS_VAL>(a);
@@ -930,4 +955,98 @@ extern "C" int wdgh_spmm_structure_fused(const int64_t *rowptr, const int32_t *c
   if (rc) return rc;
   return structure_finish(rowptr, col, n, labels, labels8, C, plan_i64, plan_host, counters, node_sum, deg_nsl,
                           match_nsl, row_offset, st);
+}
+
+// ---------------------------------------------------------------------------
+// Ranged / phased aggregation (multi-GPU overlap): see RangeArgs.
+// ---------------------------------------------------------------------------
+namespace wdgh {
+__global__ void column_segments_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
+                                       const int64_t *__restrict__ bounds, int nb, int64_t *__restrict__ seg) {
+  // seg[b][r] = first entry of row r whose column is >= bounds[b]   (thread per row, binary search per boundary)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t s = rowptr[r], e = rowptr[r + 1];
+    for (int b = 0; b < nb; ++b) {
+      const int64_t key = bounds[b];
+      int64_t lo = s, hi = e;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)col[mid] < key) lo = mid + 1;
+        else hi = mid;
+      }
+      seg[(int64_t)b * n + r] = lo;
+    }
+  }
+}
+__global__ void heavy_flags_kernel(const int64_t *__restrict__ plan, uint8_t *__restrict__ flags) {
+  const int64_t n_heavy = plan[kPlanNHeavy];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_heavy; k += stride)
+    flags[plan_heavy_row(plan)[k]] = 1;
+}
+}  // namespace wdgh
+
+extern "C" int wdgh_column_segments(const int64_t *rowptr, const int32_t *col, int64_t n, const int64_t *bounds_dev,
+                                    int32_t num_bounds, int64_t *seg, void *stream) {
+  WDGH_REQUIRE(rowptr && bounds_dev && seg && n >= 0 && num_bounds >= 1, "wdgh_column_segments: bad arguments");
+  if (n == 0) return 0;
+  column_segments_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, 0, as_stream(stream)>>>(rowptr, col, n, bounds_dev,
+                                                                                            num_bounds, seg);
+  WDGH_LAUNCHED("column_segments_kernel");
+  return 0;
+}
+
+extern "C" int wdgh_plan_heavy_flags(const int64_t *plan_i64, const int64_t *plan_host, int64_t n, uint8_t *flags,
+                                     void *stream) {
+  WDGH_REQUIRE(plan_i64 && plan_host && flags && n >= 0, "wdgh_plan_heavy_flags: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  WDGH_CUDA(cudaMemsetAsync(flags, 0, (size_t)n, st));
+  if (plan_host[0] > 0) {
+    heavy_flags_kernel<<<persistent_grid(ceil_div(plan_host[0], 256), 4), 256, 0, st>>>(plan_i64, flags);
+    WDGH_LAUNCHED("heavy_flags_kernel");
+  }
+  return 0;
+}
+
+extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, const int64_t *range_end,
+                                    const int32_t *col, const float *val, int64_t n, const float *x, int64_t d,
+                                    int64_t ldx, float *y, int64_t ldy, int norm, int add_self_loop,
+                                    const float *dinv, const uint8_t *deg_code, const uint8_t *skip_rows,
+                                    int accumulate, int finalize, int run_split_rows, const int64_t *plan_i64,
+                                    const int64_t *plan_host, float *partial, int64_t row_offset, void *stream) {
+  WDGH_REQUIRE(rowptr && range_begin && range_end && x && y && plan_i64 && plan_host, "wdgh_spmm_csr_ranged: null pointer");
+  WDGH_REQUIRE(n >= 0 && d > 0 && ldx >= d && ldy >= d, "wdgh_spmm_csr_ranged: bad shape");
+  WDGH_REQUIRE(norm == WDGH_NORM_NONE || dinv != nullptr, "wdgh_spmm_csr_ranged: norm requires dinv");
+  const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
+                    (partial == nullptr || reinterpret_cast<uintptr_t>(partial) % 16 == 0);
+  WDGH_REQUIRE(vec4 && (d >= 128 || d == 64 || d == 32) && wide_variant() == 1,
+               "wdgh_spmm_csr_ranged: needs 16-byte aligned rows and d in {32, 64} or d >= 128");
+  WDGH_REQUIRE(plan_host[1] == 0 || skip_rows != nullptr, "wdgh_spmm_csr_ranged: split rows need skip_rows (wdgh_plan_heavy_flags)");
+  if (n == 0) return 0;
+  SpmmArgs a;
+  a.rowptr = range_begin; a.col = col; a.val = val; a.n = n; a.x = x; a.d = (int)d; a.ldx = ldx; a.y = y; a.ldy = ldy;
+  a.norm = norm; a.self_loop = add_self_loop ? 1 : 0; a.dinv = dinv; a.deg_code = (val == nullptr) ? deg_code : nullptr;
+  a.plan = plan_i64;
+  a.n_heavy = plan_host[0]; a.n_chunks = plan_host[1]; a.threshold = INT64_MAX / 4;  // ranges are never "heavy" by length
+  a.n_units = 0; a.nnz = plan_host[6];
+  a.partial = partial; a.ldp = (d + 3) & ~int64_t(3);
+  a.row_offset = row_offset;
+  a.st = as_stream(stream);
+  a.ra.row_end = range_end; a.ra.skip = skip_rows; a.ra.accumulate = accumulate ? 1 : 0; a.ra.finalize = finalize ? 1 : 0;
+  a.heavy_pass = false;
+  int rc = val ? dispatch<true>(a, true) : dispatch<false>(a, true);
+  if (rc || !run_split_rows || a.n_chunks == 0) return rc;
+  // split rows: always over their full column range, after the last phase (they overwrite their Y rows)
+  WDGH_REQUIRE(partial != nullptr, "wdgh_spmm_csr_ranged: split rows need the partial buffer");
+  a.rowptr = rowptr; a.threshold = plan_host[2]; a.ra = RangeArgs{nullptr, nullptr, 0, 1};
+  if (val) {
+    if (d <= 128) return launch_heavy<4, 1, true>(a);
+    if (d <= 256) return launch_heavy<4, 2, true>(a);
+    return launch_heavy<4, 4, true>(a);
+  }
+  if (d <= 128) return launch_heavy<4, 1, false>(a);
+  if (d <= 256) return launch_heavy<4, 2, false>(a);
+  return launch_heavy<4, 4, false>(a);
 }

@@ -206,6 +206,46 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
     return y
 
 
+def column_segments(g: CSRGraph, bounds):
+    """int64 [len(bounds), n]: per row, the first stored entry whose column id is >= each bound."""
+    b = _cuda(torch.as_tensor(bounds, dtype=torch.int64), torch.int64)
+    seg = torch.empty((int(b.shape[0]), g.n), dtype=torch.int64, device=g.device)
+    check(lib.wdgh_column_segments(ptr(g.rowptr), ptr(g.col), g.n, ptr(b), int(b.shape[0]), ptr(seg), stream_ptr()),
+          "wdgh_column_segments")
+    return seg
+
+
+def heavy_flags(g: CSRGraph):
+    """uint8 [n]: 1 for the rows the plan splits into chunks."""
+    plan, plan_host = g.plan
+    flags = torch.empty(g.n, dtype=torch.uint8, device=g.device)
+    check(lib.wdgh_plan_heavy_flags(ptr(plan), plan_host, g.n, ptr(flags), stream_ptr()), "wdgh_plan_heavy_flags")
+    return flags
+
+
+def spmm_ranged(g: CSRGraph, range_begin, range_end, x, y, norm, add_self_loop, dinv, deg_code, skip_rows,
+                accumulate, finalize, run_split_rows, x_row0=0):
+    """One phase of the aggregation: entries [range_begin[r], range_end[r]) of every row (see wdgh_spmm_csr_ranged).
+
+    x_row0: global node id of x[0] -- lets a phase that only touches columns [x_row0, x_row0 + len(x)) read a
+    feature shard in place (the kernel is handed the address x[0] would have at global id 0)."""
+    d = int(x.shape[1])
+    x_ptr = x.data_ptr() - int(x_row0) * x.stride(0) * 4
+    plan, plan_host = g.plan
+    ldp = (d + 3) & ~3
+    n_part = max(g.n_chunks, 2 * g.n_units) * ldp
+    partial = g._partial.get(n_part)
+    if partial is None and n_part:
+        partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
+        g._partial = {n_part: partial}
+    check(lib.wdgh_spmm_csr_ranged(ptr(g.rowptr), ptr(range_begin), ptr(range_end), ptr(g.col), ptr(g.val), g.n,
+                                   x_ptr, d, x.stride(0), ptr(y), y.stride(0), norm, int(bool(add_self_loop)),
+                                   ptr(dinv), ptr(deg_code), ptr(skip_rows), int(bool(accumulate)), int(bool(finalize)),
+                                   int(bool(run_split_rows)), ptr(plan), plan_host, ptr(partial), g.row_offset,
+                                   stream_ptr()), "wdgh_spmm_csr_ranged")
+    return y
+
+
 # ---------------------------------------------------------------------------
 # label statistics
 # ---------------------------------------------------------------------------

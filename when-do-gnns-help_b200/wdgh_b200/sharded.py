@@ -120,7 +120,8 @@ class ShardedStats:
 class CudaShardedStats(ShardedStats):
     """The product: local compute = the CUDA kernels of libwdgh_b200.so on this rank's GPU."""
 
-    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None, slabs=None):
+    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None, slabs=None,
+                 phased=None):
         from . import graph as G
         self._G = G
         self.g = graph_local
@@ -135,6 +136,12 @@ class CudaShardedStats(ShardedStats):
         if d % slabs or (d // slabs) % 32:
             raise ValueError("feature width must split into slabs that are multiples of 32 columns")
         self.slabs = int(slabs)
+        # Phased aggregation: the entries whose source node is local are aggregated while the feature all-gather
+        # is in flight, the remote columns afterwards (two accumulate passes over Y).
+        ok_width = (d % 4 == 0) and (d >= 128 or d in (32, 64)) and graph_local.val is None
+        self.phased = bool(ok_width and world > 1 and self.slabs == 1) if phased is None else bool(phased)
+        self._seg = None
+        self._skip = None
         if graph_local.row_offset != part.bounds(rank)[0] or graph_local.n != part.rows(rank):
             raise ValueError("graph shard does not match the partition")
         super().__init__(part, rank, x_local, labels32_local, num_classes, group)
@@ -175,6 +182,8 @@ class CudaShardedStats(ShardedStats):
                 self.code_full = _all_gather_rows(_pad_rows(code, self.part.block), self.group)
         world = dist.get_world_size(self.group)
         d = int(self.x_local.shape[1])
+        if self.phased:
+            return self._step_phased(labels_full, dinv_full, norm, add_self_loop, world, d)
         ds = d // self.slabs
         if self._x_full is None:
             self._x_full = [xs.new_empty((world * xs.shape[0], ds)) for xs in self._x_slabs]
@@ -189,5 +198,82 @@ class CudaShardedStats(ShardedStats):
             work.wait()
             G.spmm(self.g, buf, norm, add_self_loop, out=self._y[:, k * ds:(k + 1) * ds], dinv=dinv_full,
                    deg_code=self.code_full)
+        counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
+        return self._y, counters, node_sum
+
+    # -- phased step: peer-mapped feature shards, copy-engine pulls, one aggregation phase per arriving shard -----
+    def reset_graph(self):
+        """The CSR arrays were overwritten in place (same shapes): drop everything derived from them."""
+        self.g._plan = None
+        self.g._dinv.clear()
+        self._seg = None
+        self._skip = None
+
+    def _setup_phased(self, world, d):
+        G = self._G
+        g = self.g
+        bounds = [b * self.part.block for b in range(world)] + [max(world * self.part.block, g.n_global)]
+        self._seg = G.column_segments(g, bounds)          # per graph, like the plan
+        self._skip = G.heavy_flags(g) if g.n_chunks else None
+        if getattr(self, "_peers_ready", False):
+            return
+        self._peers_ready = True
+        self._x_full = [self.x_local.new_empty((world * self.x_local.shape[0], d))]
+        self._peers = None
+        try:  # NVLink peer mapping of every rank's shard (torch symmetric memory): pulls run on the copy engines
+            import torch.distributed._symmetric_memory as symm_mem
+            shard = symm_mem.empty(tuple(self.x_local.shape), dtype=torch.float32, device=self.x_local.device)
+            shard.copy_(self.x_local)
+            hdl = symm_mem.rendezvous(shard, group=self.group if self.group is not None else dist.group.WORLD)
+            self._shard, self._hdl = shard, hdl
+            self._peers = [hdl.get_buffer(b, tuple(self.x_local.shape), torch.float32) for b in range(world)]
+            self.x_local = shard
+            self._copy_stream = torch.cuda.Stream()
+            self._events = [torch.cuda.Event() for _ in range(world)]
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        except Exception as e:  # no peer access: NCCL all-gather, local columns first, remote columns afterwards
+            self._peers = None
+            self._why_no_peers = repr(e)
+
+    def _step_phased(self, labels_full, dinv_full, norm, add_self_loop, world, d):
+        G = self._G
+        g, r = self.g, self.rank
+        if self._seg is None:
+            self._setup_phased(world, d)
+        x_full, seg = self._x_full[0], self._seg
+        block = self.part.block
+        if self._y is None or self._y.shape[1] != d:
+            self._y = torch.empty((g.n, d), dtype=torch.float32, device=self.x_local.device)
+        cur = torch.cuda.current_stream()
+        if self._peers is not None:
+            # pulls start once everything queued so far (the previous step still reads x_full) has finished
+            self._copy_stream.wait_stream(cur)
+            order = [(r - k) % world for k in range(1, world)]
+            with torch.cuda.stream(self._copy_stream):
+                for src in order:
+                    x_full[src * block:(src + 1) * block].copy_(self._peers[src], non_blocking=True)
+                    self._events[src].record(self._copy_stream)
+        else:
+            work = dist.all_gather_into_tensor(x_full, self.x_local, group=self.group, async_op=True)
+        # under the transfers: label pass, then the entries whose source node is local, straight from the shard
+        self._scratch = G.structure_counts_raw(g, labels_full, self.c, self._scratch)
+        G.spmm_ranged(g, seg[r], seg[r + 1], self.x_local, self._y, norm, add_self_loop, dinv_full, self.code_full,
+                      self._skip, accumulate=False, finalize=False, run_split_rows=False, x_row0=g.row_offset)
+        if self._peers is not None:
+            for i, src in enumerate(order):  # one phase per shard, in arrival order
+                cur.wait_event(self._events[src])
+                last = i == len(order) - 1
+                G.spmm_ranged(g, seg[src], seg[src + 1], x_full, self._y, norm, add_self_loop, dinv_full,
+                              self.code_full, self._skip, accumulate=True, finalize=last, run_split_rows=last)
+        else:
+            work.wait()
+            first, last = r == 0, r == world - 1
+            if not first:  # columns owned by ranks 0 .. r-1
+                G.spmm_ranged(g, seg[0], seg[r], x_full, self._y, norm, add_self_loop, dinv_full, self.code_full,
+                              self._skip, accumulate=True, finalize=last, run_split_rows=last)
+            if not last:   # columns owned by ranks r+1 .. world-1
+                G.spmm_ranged(g, seg[r + 1], seg[world], x_full, self._y, norm, add_self_loop, dinv_full,
+                              self.code_full, self._skip, accumulate=True, finalize=True, run_split_rows=True)
         counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
         return self._y, counters, node_sum
