@@ -575,3 +575,40 @@ def test_phased_aggregation_equals_one_pass(W, d, parts):
             W.graph.spmm_ranged(g, seg[r + 1], seg[parts], x, y, W.NORM_SYM, True, dinv, code, skip, True, True, True)
         err = (y - y_ref).abs().max().item()
         assert err <= 1e-5 * y_ref.abs().max().item(), (r, err)
+
+
+@pytest.mark.parametrize("d,chunks_note", [(128, "pipelined"), (96, "single copy")])
+def test_pipeline_host_entry(W, d, chunks_note):
+    """wdgh_pipeline_host (the e2e entry, host pointers in / counters + Y out) against the resident path."""
+    import ctypes as C
+    lib = W._lib.lib
+    n, c = 50000, 7
+    row, col, _ = powerlaw_graph(n, 14, seed=d)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    rng = np.random.default_rng(d)
+    labels = rng.integers(0, c, n).astype(np.int32)
+    labels[rng.random(n) < 0.1] = -1
+    x = np.ascontiguousarray(rng.standard_normal((n, d)).astype(np.float32))
+    rowptr = O.csr_from_coo(row, n)
+    col32 = np.ascontiguousarray(col.astype(np.int32))
+    y = np.empty((n, d), np.float32)
+    counters = np.zeros(W._lib.sc_words(c), np.int64)
+    node_sum = np.zeros(2, np.float64)
+    for _ in range(2):  # second call reuses the cached device buffers
+        rc = lib.wdgh_pipeline_host(rowptr.ctypes.data, col32.ctypes.data, n, col32.shape[0], x.ctypes.data, d,
+                                    labels.ctypes.data, c, W.NORM_SYM, 1, y.ctypes.data, counters.ctypes.data,
+                                    node_sum.ctypes.data)
+        assert rc == 0, lib.wdgh_last_error()
+    lib.wdgh_pipeline_host_release()
+    g = W.CSRGraph.from_csr(torch.from_numpy(rowptr), torch.from_numpy(col32), None, n)
+    assert g.n_heavy > 0
+    y_ref = W.spmm(g, torch.from_numpy(x), W.NORM_SYM, True).cpu().numpy()
+    np.testing.assert_allclose(y, y_ref, rtol=1e-5, atol=1e-5 * np.abs(y_ref).max())
+    s = W.graph.structure_counts(g, torch.from_numpy(labels).cuda(), c)
+    H = W._lib.SC_HEADER
+    assert counters[W._lib.SC_MATCH_ALL] == s.match_all and counters[W._lib.SC_N_LAB] == s.n_lab
+    assert np.array_equal(counters[H + 2 * c:H + 2 * c + c * c].reshape(c, c), s.hist)
+    assert abs(node_sum[0] - s.node_sum) <= 1e-9 * max(1.0, s.node_sum)
+    o = O.structure_counts(row, col, labels.astype(np.int64), n, num_classes=c)
+    assert np.array_equal(s.hist, o["hist"])
