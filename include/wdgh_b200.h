@@ -111,9 +111,9 @@ int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
  * D^-1/2 / D^-1 from the row lengths on the fly -- A_hat is never materialised.
  *   dinv     : float32[n] from wdgh_degree_scale (required iff norm != NONE)
  *   plan_i64 / plan_host : from wdgh_plan_build (required)
- *   partial  : float32[max(n_chunks, 2 * n_units) * roundup(d,4)] scratch: partial sums of split rows
- *              (row kernels) or of rows crossing stream-unit boundaries (nnz-balanced kernel, used when
- *              d % 4 == 0 and d >= 128); n_chunks = plan_host[1], n_units = plan_host[5]
+ *   partial  : float32[n_chunks * roundup(d,4)] scratch for the partial sums of split rows, n_chunks =
+ *              plan_host[1] (may be NULL if 0).  The experimental nnz-balanced variant (environment
+ *              WDGH_SPMM_VARIANT=2) needs max(n_chunks, 2 * plan_host[5]) rows instead.
  *   row_offset : 0 for a whole graph.  For a 1-D row shard (multi-GPU) the CSR holds rows
  *              [row_offset, row_offset + n) of the global matrix: `col`, `x` and `dinv` use global
  *              node ids, `y` is local ([n][d]).

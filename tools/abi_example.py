@@ -36,7 +36,7 @@ def sgc1_propagate(adj, x):
     code = torch.empty(n, dtype=torch.uint8, device=dev)
     assert lib.wdgh_degree_scale(rowptr.data_ptr(), None, n, 2, 1, dinv.data_ptr(), None, code.data_ptr(), st) == 0
     y = torch.empty_like(x)
-    n_part = max(plan_host[1], 2 * plan_host[5]) * ((d + 3) & ~3)                           # scratch for split rows
+    n_part = plan_host[1] * ((d + 3) & ~3)                                                   # scratch for split rows
     partial = torch.empty(max(n_part, 1), dtype=torch.float32, device=dev)
     rc = lib.wdgh_spmm_csr(rowptr.data_ptr(), col.data_ptr(), None, n, x.data_ptr(), d, x.stride(0), y.data_ptr(), d,
                            2, 1, dinv.data_ptr(), code.data_ptr(), plan.data_ptr(), plan_host, partial.data_ptr(), 0, st)

@@ -126,7 +126,9 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   int rc = wdgh_plan_build(c.rowptr, n, nnz, kHostPipelineThreshold, c.plan, cap, plan_host, st);
   if (rc) return rc;
   const int64_t ldp = (d + 3) & ~int64_t(3);
-  const int64_t n_part = plan_host[1] > 2 * plan_host[5] ? plan_host[1] : 2 * plan_host[5];
+  const char *variant = getenv("WDGH_SPMM_VARIANT");  // the experimental stream variant needs 2 rows per unit
+  const int64_t units2 = (variant && atoi(variant) == 2) ? 2 * plan_host[5] : 0;
+  const int64_t n_part = plan_host[1] > units2 ? plan_host[1] : units2;
   if (n_part * ldp > c.partial_elems) {
     cudaFree(c.partial);
     c.partial = nullptr;

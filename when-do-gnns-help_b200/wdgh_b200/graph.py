@@ -190,12 +190,7 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
     if y.shape != (g.n, d) or y.stride(1) != 1:
         raise ValueError("out must be [n, d] with unit column stride (a column slab of a wider matrix is fine)")
     plan, plan_host = g.plan
-    ldp = (d + 3) & ~3
-    n_part = max(g.n_chunks, 2 * g.n_units) * ldp  # scratch for rows split across chunks / stream units
-    partial = g._partial.get(n_part)
-    if partial is None and n_part:
-        partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
-        g._partial = {n_part: partial}
+    partial = _partial_scratch(g, d)
     if norm != NORM_NONE and dinv is None:
         if g.n_global != g.n:
             raise ValueError("a row shard needs the all-gathered degree scale (dinv=...)")
@@ -204,6 +199,20 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
                             norm, int(bool(add_self_loop)), ptr(dinv), ptr(deg_code), ptr(plan), plan_host,
                             ptr(partial), g.row_offset, stream_ptr()), "wdgh_spmm_csr")
     return y
+
+
+def _partial_scratch(g: CSRGraph, d: int):
+    """Scratch for rows whose sum is assembled from pieces: split rows (n_chunks x d) and, only for the experimental
+    nnz-balanced stream variant (WDGH_SPMM_VARIANT=2), two partial rows per 1024-entry stream unit."""
+    import os
+    ldp = (d + 3) & ~3
+    units = 2 * g.n_units if os.environ.get("WDGH_SPMM_VARIANT") == "2" else 0
+    n_part = max(g.n_chunks, units) * ldp
+    partial = g._partial.get(n_part)
+    if partial is None and n_part:
+        partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
+        g._partial = {n_part: partial}
+    return partial
 
 
 def column_segments(g: CSRGraph, bounds):
@@ -232,12 +241,7 @@ def spmm_ranged(g: CSRGraph, range_begin, range_end, x, y, norm, add_self_loop, 
     d = int(x.shape[1])
     x_ptr = x.data_ptr() - int(x_row0) * x.stride(0) * 4
     plan, plan_host = g.plan
-    ldp = (d + 3) & ~3
-    n_part = max(g.n_chunks, 2 * g.n_units) * ldp
-    partial = g._partial.get(n_part)
-    if partial is None and n_part:
-        partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
-        g._partial = {n_part: partial}
+    partial = _partial_scratch(g, d)
     check(lib.wdgh_spmm_csr_ranged(ptr(g.rowptr), ptr(range_begin), ptr(range_end), ptr(g.col), ptr(g.val), g.n,
                                    x_ptr, d, x.stride(0), ptr(y), y.stride(0), norm, int(bool(add_self_loop)),
                                    ptr(dinv), ptr(deg_code), ptr(skip_rows), int(bool(accumulate)), int(bool(finalize)),
@@ -354,12 +358,7 @@ def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, a
                    torch.empty(n_labels, dtype=torch.uint8, device=dev))
     counters, node_sum, deg, match, lab8 = scratch
     plan, plan_host = g.plan
-    ldp = (d + 3) & ~3
-    n_part = max(g.n_chunks, 2 * g.n_units) * ldp
-    partial = g._partial.get(n_part)
-    if partial is None and n_part:
-        partial = torch.empty(n_part, dtype=torch.float32, device=dev)
-        g._partial = {n_part: partial}
+    partial = _partial_scratch(g, d)
     if norm != NORM_NONE and dinv is None:
         dinv, _, deg_code = g.degree_scale(norm, add_self_loop)
     check(lib.wdgh_spmm_structure_fused(ptr(g.rowptr), ptr(g.col), g.n, g.nnz, ptr(x), d, x.stride(0), ptr(y),
