@@ -1,0 +1,52 @@
+"""Host-side logic of the mirror that needs no GPU: RNG-compatible splits, accuracy, masks."""
+import numpy as np
+import torch
+
+from oracle import ref_port as O
+
+
+def test_splits_consume_rng_like_the_reference():
+    from wdgh_b200 import util_funcs as uf
+    labels = torch.from_numpy(np.random.default_rng(0).integers(0, 5, 1000))
+    for pct in (0.6, 0.3):
+        torch.manual_seed(123)
+        a = uf.random_disassortative_splits(labels, torch.tensor(5), pct)
+        after_a = torch.rand(1)
+        torch.manual_seed(123)
+        b = O.random_disassortative_splits(labels, 5, pct)
+        after_b = torch.rand(1)
+        for m1, m2 in zip(a, b):
+            assert m1.dtype == torch.bool and torch.equal(m1, m2)
+        assert torch.equal(after_a, after_b)          # same number of RNG draws
+        tr, va, te = a
+        assert not (tr & va).any() and not (tr & te).any() and not (va & te).any()
+        assert int(tr.sum() + va.sum() + te.sum()) == 1000
+        assert int(va.sum()) == 200
+
+
+def test_accuracy_and_mask():
+    from wdgh_b200 import util_funcs as uf
+    out = torch.tensor([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7], [0.6, 0.4]])
+    labels = torch.tensor([1, 0, 0, 0])
+    assert float(uf.accuracy(labels, out)) == float(O.accuracy(labels, out)) == 0.75
+    m = uf.index_to_mask(torch.tensor([0, 3]), 5)
+    assert m.tolist() == [True, False, False, True, False]
+
+
+def test_rand_train_test_idx_partitions_labelled_nodes():
+    from wdgh_b200 import util_funcs as uf
+    label = torch.tensor([0, 1, -1, 1, 0, -1, 1, 0, 0, 1])
+    np.random.seed(4)
+    tr, va, te = uf.rand_train_test_idx(label)
+    allidx = torch.cat([tr, va, te]).sort().values
+    assert allidx.tolist() == [0, 1, 3, 4, 6, 7, 8, 9]
+    assert len(tr) == 4 and len(va) == 1
+    np.random.seed(4)
+    perm = np.random.permutation(8)
+    assert tr.tolist() == torch.where(label != -1)[0][perm[:4]].tolist()
+
+
+def test_row_partition_is_used_by_bench_defaults():
+    from wdgh_b200.sharded import RowPartition
+    p = RowPartition(50_000_000, 8)
+    assert p.block == 6_250_000 and p.bounds(7) == (43_750_000, 50_000_000)

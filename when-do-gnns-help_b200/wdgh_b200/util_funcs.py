@@ -55,46 +55,48 @@ def propagate(adj, features, symmetric=1, add_self_loop=True):
 
 
 def accuracy(labels, output):
-    """util_funcs.py:393-397."""
-    preds = output.max(1)[1].type_as(labels)
-    correct = preds.eq(labels).double()
-    return correct.sum() / len(labels)
+    """Fraction of rows whose arg-max equals the label, as a float64 tensor.  util_funcs.py:393-397."""
+    predicted = torch.argmax(output, dim=1).to(labels.dtype)
+    return (predicted == labels).double().sum() / len(labels)
 
 
 def index_to_mask(index, size):
-    """util_funcs.py:478-481."""
+    """Boolean mask of length `size` that is True at `index`.  util_funcs.py:478-481."""
     mask = torch.zeros(size, dtype=torch.bool, device=index.device)
-    mask[index] = 1
+    mask[index] = True
     return mask
 
 
 def random_disassortative_splits(labels, num_classes, training_percentage=0.6):
-    """util_funcs.py:454-475: class-balanced 60/20/20 masks; same torch.randperm call sequence."""
+    """Class-balanced train / val / test masks (60 / 20 / 20 by default).  util_funcs.py:454-475.
+
+    Consumes torch's global RNG in the reference's order -- one `randperm` per class over that class's
+    nodes, then one over the left-over nodes -- so seeded runs pick the same nodes as the reference."""
     labels = torch.as_tensor(labels).cpu()
-    num_classes = int(num_classes)
-    indices = []
-    for i in range(num_classes):
-        index = torch.nonzero((labels == i)).view(-1)
-        index = index[torch.randperm(index.size(0))]
-        indices.append(index)
-    percls_trn = int(round(training_percentage * (labels.size()[0] / num_classes)))
-    val_lb = int(round(0.2 * labels.size()[0]))
-    train_index = torch.cat([i[:percls_trn] for i in indices], dim=0)
-    rest_index = torch.cat([i[percls_trn:] for i in indices], dim=0)
-    rest_index = rest_index[torch.randperm(rest_index.size(0))]
-    train_mask = index_to_mask(train_index, size=labels.size()[0])
-    val_mask = index_to_mask(rest_index[:val_lb], size=labels.size()[0])
-    test_mask = index_to_mask(rest_index[val_lb:], size=labels.size()[0])
-    return train_mask, val_mask, test_mask
+    n = labels.shape[0]
+    k = int(num_classes)
+    per_class = int(round(training_percentage * (n / k)))
+    n_val = int(round(0.2 * n))
+    train_parts, rest_parts = [], []
+    for cls in range(k):
+        members = torch.nonzero(labels == cls).view(-1)
+        shuffled = members[torch.randperm(members.size(0))]
+        train_parts.append(shuffled[:per_class])
+        rest_parts.append(shuffled[per_class:])
+    train_index = torch.cat(train_parts, dim=0)
+    rest = torch.cat(rest_parts, dim=0)
+    rest = rest[torch.randperm(rest.size(0))]
+    return index_to_mask(train_index, n), index_to_mask(rest[:n_val], n), index_to_mask(rest[n_val:], n)
 
 
 def rand_train_test_idx(label, train_prop=.6, valid_prop=.2, ignore_negative=True):
-    """util_funcs.py:484-508."""
-    labeled_nodes = torch.where(label != -1)[0] if ignore_negative else label
-    n = labeled_nodes.shape[0]
-    train_num, valid_num = int(n * train_prop), int(n * valid_prop)
-    perm = torch.as_tensor(np.random.permutation(n))
-    train_indices, val_indices, test_indices = perm[:train_num], perm[train_num:train_num + valid_num], perm[train_num + valid_num:]
+    """Random train / valid / test index split over the labelled nodes (label != -1).  util_funcs.py:484-508.
+    Uses numpy's global RNG (`np.random.permutation`) like the reference."""
+    pool = torch.where(label != -1)[0] if ignore_negative else label
+    count = pool.shape[0]
+    n_train, n_valid = int(count * train_prop), int(count * valid_prop)
+    order = torch.as_tensor(np.random.permutation(count))
+    parts = (order[:n_train], order[n_train:n_train + n_valid], order[n_train + n_valid:])
     if not ignore_negative:
-        return train_indices, val_indices, test_indices
-    return labeled_nodes[train_indices], labeled_nodes[val_indices], labeled_nodes[test_indices]
+        return parts
+    return tuple(pool[p] for p in parts)
