@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-sample-nodes", type=int, default=1_000_000)
     ap.add_argument("--slabs", type=int, default=0, help="feature column slabs for the N>1 pipeline (0 = default)")
     ap.add_argument("--no-phased", action="store_true", help="N>1: plain all-gather then aggregate (no overlap)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "1d", "2d"],
+                    help="N>1: 1-D row partition or 2-D (2 row groups x N/2 column groups); auto = 2d for N >= 4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -206,7 +208,9 @@ def workload_config(args, nnz):
                         f"{args.nodes} nodes, avg row length {args.avg_degree:g}, d={args.dim} f32, "
                         f"{args.classes} classes, h={args.homophily}",
             "nodes": args.nodes, "stored_entries": nnz, "dim": args.dim, "classes": args.classes,
-            "norm": "sym D^-1/2 (A+I) D^-1/2 on the fly", "partition": f"rows/{args.gpus}",
+            "norm": "sym D^-1/2 (A+I) D^-1/2 on the fly",
+            "partition": (f"rows/{args.gpus}" if not getattr(args, "_use_2d", False) else
+                          f"2 row groups x {args.gpus // 2} column groups"),
             "l2_policy": "inputs (feature matrix >= 25 GB at full size) are far larger than the 126 MB L2"}
 
 
@@ -239,11 +243,39 @@ def main():
     nnz_local = int(col.shape[0])
     g = G.CSRGraph(rowptr, col, None, r1 - r0, row_offset=r0, n_global=n)
     _ = g.plan  # degree binning: built once per resident graph
+    use_2d = world >= 4 and world % 2 == 0 and (args.partition == "2d" or (args.partition == "auto" and d % 4 == 0
+                                                                           and (d >= 128 or d in (32, 64))))
+    if args.partition == "2d" and not use_2d:
+        raise SystemExit("--partition 2d needs an even number of at least 4 GPUs")
+    slice_graphs = None
+    args._use_2d = use_2d
+    if use_2d:
+        from wdgh_b200.sharded import Cuda2DShardedStats, Grid2D
+        grid2 = Grid2D(n, world, 2)
+        gi, gj = grid2.coords(rank)
+        slice_graphs = []
+        for srank in grid2.row_group_ranks(gi):      # rows of every rank of my row group, columns of my column group
+            s0, s1 = part.bounds(srank)
+            if srank == rank:
+                rp_s, col_s = rowptr, col
+            else:
+                rp_s, col_s, _, _ = gen_rows(s0, s1, n, args.avg_degree, C, args.homophily, d, device, want_x=False)
+            keep = grid2.col_in_group(col_s.to(torch.int64), gj)
+            rid = torch.repeat_interleave(torch.arange(s1 - s0, device=device), rp_s[1:] - rp_s[:-1])
+            cnt = torch.bincount(rid[keep], minlength=s1 - s0)
+            rp_f = torch.zeros(s1 - s0 + 1, dtype=torch.int64, device=device)
+            rp_f[1:] = torch.cumsum(cnt, 0)
+            sg = G.CSRGraph(rp_f, col_s[keep].contiguous(), None, s1 - s0, row_offset=s0, n_global=n)
+            _ = sg.plan
+            slice_graphs.append(sg)
+            del keep, rid, cnt
+        torch.cuda.empty_cache()
     nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(nnz_t)
     nnz = int(nnz_t.item())
 
+    pipe = None
     if world == 1:
         y = torch.empty((n, d), dtype=torch.float32, device=device)
         scratch = [None]
@@ -255,8 +287,11 @@ def main():
                                                    deg_code=code, scratch=scratch[0])
             return scratch[0][0], scratch[0][1]
     else:
-        pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C, slabs=(args.slabs or None),
-                                phased=(False if args.no_phased else None))
+        if use_2d:
+            pipe = Cuda2DShardedStats(grid2, rank, slice_graphs, g, x_local, labels_local, C)
+        else:
+            pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C, slabs=(args.slabs or None),
+                                    phased=(False if args.no_phased else None))
 
         def step():
             _, counters, node_sum = pipe.step(W.NORM_SYM, True)
@@ -292,26 +327,49 @@ def main():
         xs = x_local
         dinv, _, code = g.degree_scale(W.NORM_SYM, True)
         ys = y
-    else:
+    elif not use_2d:
         xs, _, dinv = pipe.gather_inputs(W.NORM_SYM, True)
         code = pipe.code_full
         ys = torch.empty((g.n, d), dtype=torch.float32, device=device)
+    if use_2d:
+        # the aggregation kernels of this rank's block (pc row slices, raw partial sums), features already gathered
+        dinv2, _, code2 = g.degree_scale(W.NORM_SYM, True)
+        blk = part.block
+        dinv_f = torch.zeros(world * blk, dtype=torch.float32, device=device)
+        code_f = torch.zeros(world * blk, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(dinv_f, torch.nn.functional.pad(dinv2, (0, blk - dinv2.shape[0])))
+        dist.all_gather_into_tensor(code_f, torch.nn.functional.pad(code2, (0, blk - code2.shape[0])))
+
+        def spmm_once():
+            for si, sg in enumerate(slice_graphs):
+                G.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], pipe.x_full, pipe.partial[si], W.NORM_SYM, True,
+                              dinv_f, code_f, pipe._skip[si], False, False, True)
+        nnz_local = sum(sg.nnz for sg in slice_graphs)
+        rows_local = sum(sg.n for sg in slice_graphs)
+    else:
+        def spmm_once():
+            G.spmm(g, xs, W.NORM_SYM, True, out=ys, dinv=dinv, deg_code=code)
+        rows_local = r1 - r0
+    if getattr(pipe, "stage_ms", None) and os.environ.get("WDGH_STAGE_TIMES") == "1":
+        print(f"[rank {rank}] stages: " + ", ".join(f"{k} {v:.2f}" for k, v in pipe.stage_ms), file=sys.stderr, flush=True)
     for _ in range(2):
-        G.spmm(g, xs, W.NORM_SYM, True, out=ys, dinv=dinv, deg_code=code)
+        spmm_once()
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = max(3, min(args.steps, 10))
     k0.record()
     for _ in range(reps):
-        G.spmm(g, xs, W.NORM_SYM, True, out=ys, dinv=dinv, deg_code=code)
+        spmm_once()
     k1.record()
     torch.cuda.synchronize()
     spmm_ms = k0.elapsed_time(k1) / reps
-    rows_local = r1 - r0
     # algorithmic bytes of one SpMM launch (DESIGN.md "SpMM roofline"): per stored entry a 4 B column id,
     # a 4 B D^-1/2 gather and a d*4 B feature-row gather; per row 8 B rowptr, 4 B scale, d*4 B self-loop
-    # row and d*4 B output row.
-    alg_bytes = nnz_local * (4 + 4 + 4 * d) + rows_local * (8 + 4 + 4 * d + 4 * d)
+    # row and d*4 B output row (2-D partition: raw partial rows, no scale / self-loop read).
+    if use_2d:
+        alg_bytes = nnz_local * (4 + 4 + 4 * d) + rows_local * (8 + 4 * d)
+    else:
+        alg_bytes = nnz_local * (4 + 4 + 4 * d) + rows_local * (8 + 4 + 4 * d + 4 * d)
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:

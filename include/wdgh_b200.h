@@ -136,7 +136,8 @@ int wdgh_plan_heavy_flags(const int64_t *plan_i64, const int64_t *plan_host, int
 /* wdgh_spmm_csr restricted to the entries [range_begin[r], range_end[r]) of every row r:
  *   accumulate != 0 : y += (instead of y =);   finalize != 0 : apply the self loop and the row scale now
  *   (earlier phases store raw partial sums);   run_split_rows != 0 : afterwards compute the split rows over their
- *   full column range (they need all of x).  Needs 16-byte aligned rows and d in {32, 64} or d >= 128. */
+ *   full column range (they need all of x; finalized or raw like the call).
+ * Needs 16-byte aligned rows and d in {32, 64} or d >= 128. */
 int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, const int64_t *range_end,
                          const int32_t *col, const float *val, int64_t n,
                          const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
@@ -144,6 +145,13 @@ int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, cons
                          const uint8_t *skip_rows, int accumulate, int finalize, int run_split_rows,
                          const int64_t *plan_i64, const int64_t *plan_host, float *partial,
                          int64_t row_offset, void *stream);
+
+/* 2-D partition epilogue: y[r] = s_r * (sum_p parts[p][r] + [self loop] t_r * x[r + row_offset]) for `rows` rows, where
+ * parts are raw partial aggregations (wdgh_spmm_csr_ranged with finalize = 0) of the same rows over disjoint column
+ * groups (own partial + slices pulled from peers).  parts_host: HOST array of n_parts (<= 16) device pointers. */
+int wdgh_reduce_finalize(const float *const *parts_host, int32_t n_parts, int64_t rows, int64_t d, int64_t ld_parts,
+                         const float *x, int64_t ldx, float *y, int64_t ldy,
+                         int norm, int add_self_loop, const float *dinv, int64_t row_offset, void *stream);
 
 /* ---- label metrics: one pass over the edges ------------------------------ */
 /* Integer statistics every label metric of homophily_metrics.py is a ratio of

@@ -577,6 +577,57 @@ def test_phased_aggregation_equals_one_pass(W, d, parts):
         assert err <= 1e-5 * y_ref.abs().max().item(), (r, err)
 
 
+@pytest.mark.parametrize("d,world,n", [(128, 4, 20000), (64, 8, 20003)])
+def test_2d_partition_blocks_reduce_to_one_pass(W, d, world, n):
+    """Single-GPU replay of the 2-D partition: every rank's block as raw partial sums per row slice
+    (wdgh_spmm_csr_ranged, finalize=0, split rows included), then wdgh_reduce_finalize at the owner == one SpMM."""
+    from wdgh_b200.sharded import Grid2D
+    row, col, _ = powerlaw_graph(n, 10, seed=d)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    x = torch.from_numpy(np.random.default_rng(d).standard_normal((n, d)).astype(np.float32)).cuda()
+    g = W.CSRGraph.from_coo_indices(torch.from_numpy(np.vstack([row, col])), None, n, threshold=256)
+    y_ref = W.spmm(g, x, W.NORM_SYM, True)
+    dinv, _, code = g.degree_scale(W.NORM_SYM, True)
+    grid = Grid2D(n, world, 2)
+    blk, pc = grid.part.block, grid.pc
+    n_pad = world * blk
+    x_pad = torch.zeros((n_pad, d), device="cuda")
+    x_pad[:n] = x
+    dinv_pad = torch.zeros(n_pad, device="cuda")
+    dinv_pad[:n] = dinv
+    code_pad = torch.zeros(n_pad, dtype=torch.uint8, device="cuda")
+    code_pad[:n] = code
+    rowptr, colg = g.rowptr.cpu().numpy(), g.col.cpu().numpy()
+    n_heavy = 0
+    for owner in range(world):
+        r0, r1 = grid.part.bounds(owner)
+        i, s = grid.coords(owner)
+        parts = []
+        for j in range(pc):     # producer rank (i, j): rows of `owner`, columns of column group j
+            lo, hi = rowptr[r0], rowptr[r1]
+            c_s = colg[lo:hi]
+            rid = np.repeat(np.arange(r1 - r0), np.diff(rowptr[r0:r1 + 1]))
+            m = grid.col_in_group(torch.from_numpy(c_s.astype(np.int64)), j).numpy()
+            rp = np.zeros(r1 - r0 + 1, np.int64)
+            rp[1:] = np.cumsum(np.bincount(rid[m], minlength=r1 - r0))
+            sg = W.CSRGraph(torch.from_numpy(rp).cuda(), torch.from_numpy(c_s[m]).cuda(), None, r1 - r0,
+                            row_offset=r0, n_global=n, threshold=64)
+            n_heavy += sg.n_heavy
+            skip = W.graph.heavy_flags(sg) if sg.n_chunks else None
+            # degree codes are optional for the ranged entry: exercise both forms
+            dcode = code_pad if world == 8 else None
+            part = torch.full((blk, d), float("nan"), device="cuda")
+            W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_pad, part, W.NORM_SYM, True, dinv_pad, dcode, skip,
+                                False, False, True)
+            parts.append(part)
+        y = torch.empty((r1 - r0, d), device="cuda")
+        W.graph.reduce_finalize(parts, x_pad, y, W.NORM_SYM, True, dinv_pad, r0)
+        err = (y - y_ref[r0:r1]).abs().max().item()
+        assert err <= 1e-5 * y_ref.abs().max().item(), (owner, err)
+    assert n_heavy > 0
+
+
 @pytest.mark.parametrize("d,chunks_note", [(128, "pipelined"), (96, "single copy")])
 def test_pipeline_host_entry(W, d, chunks_note):
     """wdgh_pipeline_host (the e2e entry, host pointers in / counters + Y out) against the resident path."""

@@ -50,3 +50,22 @@ def test_row_partition_is_used_by_bench_defaults():
     from wdgh_b200.sharded import RowPartition
     p = RowPartition(50_000_000, 8)
     assert p.block == 6_250_000 and p.bounds(7) == (43_750_000, 50_000_000)
+
+
+def test_grid2d_blocks_tile_the_matrix():
+    """Every (row, column) pair falls into exactly one rank's block; groups have the documented members."""
+    from wdgh_b200.sharded import Grid2D
+    g = Grid2D(1000, 8, 2)
+    assert (g.pr, g.pc) == (2, 4) and g.coords(6) == (1, 2)
+    assert g.row_group_ranks(1) == [4, 5, 6, 7] and g.col_group_ranks(2) == [2, 6]
+    col = torch.arange(1000)
+    owner = col // g.part.block
+    hits = torch.zeros(1000, dtype=torch.int64)
+    for j in range(g.pc):
+        m = g.col_in_group(col, j)
+        assert set(owner[m].tolist()) <= set(g.col_group_ranks(j))
+        hits += m
+    assert bool((hits == 1).all())
+    # ranks of a row group cover the rows of that group once each
+    rows = sorted(r for s in g.row_group_ranks(0) for r in range(*g.part.bounds(s)))
+    assert rows == list(range(0, 4 * g.part.block))

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128)
 spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__restrict__ x, int d, int64_t ldx,
                          float *__restrict__ y, int64_t ldy, int norm, int self_loop,
                          const float *__restrict__ dinv, const int64_t *__restrict__ plan,
-                         const float *__restrict__ partial, int64_t ldp, int64_t row_offset) {
+                         const float *__restrict__ partial, int64_t ldp, int64_t row_offset, int finalize) {
   const int64_t k = blockIdx.x;
   const int64_t cap = plan[kPlanCapacity], T = plan[kPlanThreshold];
   const int64_t row = plan_heavy_row(plan)[k];
@@ -212,13 +212,13 @@ spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__rest
   const int64_t deg = __ldg(rowptr + row + 1) - __ldg(rowptr + row);
   const int64_t nch = (deg + T - 1) / T;
   const int64_t grow = row + row_offset;
-  const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + grow) : 1.f;
+  const float si = (norm != WDGH_NORM_NONE && finalize) ? __ldg(dinv + grow) : 1.f;
   const float self_w = (norm == WDGH_NORM_SYM) ? si : 1.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float acc = 0.f;
     for (int64_t p = 0; p < nch; ++p) acc += partial[(c0 + p) * ldp + c];
-    if (self_loop) acc = fmaf(self_w, __ldg(x + grow * ldx + c), acc);
-    y[row * ldy + c] = acc * si;
+    if (self_loop && finalize) acc = fmaf(self_w, __ldg(x + grow * ldx + c), acc);
+    y[row * ldy + c] = acc * si;  // finalize == 0: the raw partial sum (2-D partition: reduced across ranks later)
   }
 }
 
@@ -737,7 +737,7 @@ static int launch_heavy(const SpmmArgs &a) {
   WDGH_LAUNCHED("spmm_chunks_kernel");
   spmm_heavy_finish_kernel<<<(unsigned)a.n_heavy, 128, 0, a.st>>>(a.rowptr, a.x, a.d, a.ldx, a.y, a.ldy, a.norm,
                                                                   a.self_loop, a.dinv, a.plan, a.partial, a.ldp,
-                                                                  a.row_offset);
+                                                                  a.row_offset, a.ra.finalize);
   WDGH_LAUNCHED("spmm_heavy_finish_kernel");
   return 0;
 }
@@ -1040,7 +1040,7 @@ extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_
   if (rc || !run_split_rows || a.n_chunks == 0) return rc;
   // split rows: always over their full column range, after the last phase (they overwrite their Y rows)
   WDGH_REQUIRE(partial != nullptr, "wdgh_spmm_csr_ranged: split rows need the partial buffer");
-  a.rowptr = rowptr; a.threshold = plan_host[2]; a.ra = RangeArgs{nullptr, nullptr, 0, 1};
+  a.rowptr = rowptr; a.threshold = plan_host[2]; a.ra = RangeArgs{nullptr, nullptr, 0, finalize ? 1 : 0};
   if (val) {
     if (d <= 128) return launch_heavy<4, 1, true>(a);
     if (d <= 256) return launch_heavy<4, 2, true>(a);
@@ -1049,4 +1049,54 @@ extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_
   if (d <= 128) return launch_heavy<4, 1, false>(a);
   if (d <= 256) return launch_heavy<4, 2, false>(a);
   return launch_heavy<4, 4, false>(a);
+}
+
+// ---------------------------------------------------------------------------
+// 2-D partition: y[r] = s_r * (sum_p part_p[r] + [self loop] t_r * x[r]) for a row slice -- the reduction of the
+// partial aggregations of one row group (own partial + the slices pulled from the peers) fused with the epilogue.
+// ---------------------------------------------------------------------------
+namespace wdgh {
+struct PartPtrs {
+  const float *p[16];
+};
+__global__ void __launch_bounds__(256)
+reduce_finalize_kernel(PartPtrs parts, int n_parts, int64_t rows, int d4, int64_t ldp4, const float *__restrict__ x,
+                       int64_t ldx4, float *__restrict__ y, int64_t ldy4, int norm, int self_loop,
+                       const float *__restrict__ dinv, int64_t row_offset) {
+  const int64_t total = rows * d4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t r = t / d4;
+    const int c = (int)(t - r * d4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < n_parts; ++p) {
+      const float4 v = ldg_na(reinterpret_cast<const float4 *>(parts.p[p]) + r * ldp4 + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float si = (norm != WDGH_NORM_NONE) ? __ldg(dinv + r + row_offset) : 1.f;
+    if (self_loop) {
+      const float sw = (norm == WDGH_NORM_SYM) ? si : 1.f;
+      const float4 xi = ldg_na(reinterpret_cast<const float4 *>(x) + (r + row_offset) * ldx4 + c);
+      acc.x = fmaf(sw, xi.x, acc.x); acc.y = fmaf(sw, xi.y, acc.y); acc.z = fmaf(sw, xi.z, acc.z); acc.w = fmaf(sw, xi.w, acc.w);
+    }
+    acc.x *= si; acc.y *= si; acc.z *= si; acc.w *= si;
+    st_cs(reinterpret_cast<float4 *>(y) + r * ldy4 + c, acc);
+  }
+}
+}  // namespace wdgh
+
+extern "C" int wdgh_reduce_finalize(const float *const *parts_host, int32_t n_parts, int64_t rows, int64_t d,
+                                    int64_t ld_parts, const float *x, int64_t ldx, float *y, int64_t ldy, int norm,
+                                    int add_self_loop, const float *dinv, int64_t row_offset, void *stream) {
+  WDGH_REQUIRE(parts_host && n_parts >= 1 && n_parts <= 16 && y && rows >= 0 && d > 0, "wdgh_reduce_finalize: bad arguments");
+  WDGH_REQUIRE(d % 4 == 0 && ld_parts % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "wdgh_reduce_finalize: needs 16-byte rows");
+  WDGH_REQUIRE(norm == WDGH_NORM_NONE || dinv != nullptr, "wdgh_reduce_finalize: norm requires dinv");
+  WDGH_REQUIRE(!add_self_loop || x != nullptr, "wdgh_reduce_finalize: self loop requires x");
+  if (rows == 0) return 0;
+  PartPtrs pp;
+  for (int i = 0; i < 16; ++i) pp.p[i] = i < n_parts ? parts_host[i] : nullptr;
+  reduce_finalize_kernel<<<persistent_grid(ceil_div(rows * (d / 4), 256), 8), 256, 0, as_stream(stream)>>>(
+      pp, n_parts, rows, (int)(d / 4), ld_parts / 4, x, ldx / 4, y, ldy / 4, norm, add_self_loop ? 1 : 0, dinv, row_offset);
+  WDGH_LAUNCHED("reduce_finalize_kernel");
+  return 0;
 }

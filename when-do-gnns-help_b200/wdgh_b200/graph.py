@@ -250,6 +250,19 @@ def spmm_ranged(g: CSRGraph, range_begin, range_end, x, y, norm, add_self_loop, 
     return y
 
 
+def reduce_finalize(parts, x, y, norm, add_self_loop, dinv, row_offset):
+    """y[r] = s_r * (sum_p parts[p][r] + self loop) -- epilogue of the 2-D partition (see wdgh_reduce_finalize)."""
+    rows, d = int(y.shape[0]), int(y.shape[1])
+    arr = (C.c_void_p * len(parts))(*[p.data_ptr() for p in parts])
+    ld = parts[0].stride(0)
+    assert all(p.stride(0) == ld and p.shape[0] >= rows and p.shape[1] == d for p in parts)
+    check(lib.wdgh_reduce_finalize(C.cast(arr, C.c_void_p), len(parts), rows, d, ld, ptr(x),
+                                   x.stride(0) if x is not None else d, ptr(y), y.stride(0), norm,
+                                   int(bool(add_self_loop)), ptr(dinv), int(row_offset), stream_ptr()),
+          "wdgh_reduce_finalize")
+    return y
+
+
 # ---------------------------------------------------------------------------
 # label statistics
 # ---------------------------------------------------------------------------

@@ -12,6 +12,8 @@ through two methods so that the world_size-2 gloo tests can drive the same plumb
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -276,4 +278,146 @@ class CudaShardedStats(ShardedStats):
                 G.spmm_ranged(g, seg[r + 1], seg[world], x_full, self._y, norm, add_self_loop, dinv_full,
                               self.code_full, self._skip, accumulate=True, finalize=True, run_split_rows=True)
         counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
+        return self._y, counters, node_sum
+
+
+# ===============================================================================================
+# 2-D (row group x column group) partition: less NVLink traffic than the 1-D row partition
+# ===============================================================================================
+class Grid2D:
+    """world = pr x pc ranks; rank r = i * pc + j sits in row group i and column group j.
+
+    Nodes stay owned 1-D (rank r owns [r*block, (r+1)*block)).  Row group i = the rows of ranks i*pc .. i*pc+pc-1;
+    column group j = the nodes owned by the ranks with (rank % pc) == j.  Rank (i, j) aggregates the block
+    A[rows of group i, columns of group j]: it needs only the feature shards of its column group (pr shards
+    instead of all pr*pc) and produces partial sums for the rows of its whole row group, which are then reduced
+    onto the owner of each row slice."""
+
+    def __init__(self, n: int, world: int, pr: int):
+        if world % pr:
+            raise ValueError("world must be a multiple of pr")
+        self.n, self.world, self.pr, self.pc = int(n), int(world), int(pr), world // pr
+        self.part = RowPartition(n, world)
+
+    def coords(self, rank: int):
+        return rank // self.pc, rank % self.pc
+
+    def row_group_ranks(self, i: int):
+        return [i * self.pc + s for s in range(self.pc)]
+
+    def col_group_ranks(self, j: int):
+        return [ii * self.pc + j for ii in range(self.pr)]
+
+    def col_in_group(self, col, j: int):
+        """Boolean mask: which column ids belong to column group j."""
+        return (col // max(self.part.block, 1)) % self.pc == j
+
+
+class Cuda2DShardedStats:
+    """A_hat X on the 2-D partition + label statistics on the 1-D row shard (see Grid2D).
+
+    Per step: pull the partner shards of the column group (copy engines, peer-mapped memory) while the label pass
+    runs; aggregate the pc row slices of the block one after the other (raw partial sums), PUSHING each finished
+    foreign slice into its owner's receive buffer with the copy engines while the next slice is aggregated; one
+    tiny all-reduce as barrier; `wdgh_reduce_finalize` sums own + received partials and applies self loop + scale."""
+
+    def __init__(self, grid: Grid2D, rank: int, slice_graphs, graph_1d, x_local, labels32_local, num_classes, group=None):
+        from . import graph as G
+        import torch.distributed._symmetric_memory as symm_mem
+        self._G, self.grid, self.rank, self.group = G, grid, rank, group
+        self.i, self.j = grid.coords(rank)
+        self.slices = slice_graphs          # pc CSRGraphs: rows of rank i*pc+s, columns of group j (global ids)
+        self.g1d = graph_1d                 # rows of this rank, all columns (label pass, degree scale)
+        self.c = int(num_classes)
+        part, pc = grid.part, grid.pc
+        blk, d = part.block, int(x_local.shape[1])
+        dev = x_local.device
+        self.labels_local = _pad_rows(labels32_local, blk)
+        wgroup = group if group is not None else dist.group.WORLD
+        # symmetric (peer-mapped) buffers.  x_full is indexed by global node id; my own shard lives in place at
+        # rows [rank*blk, (rank+1)*blk) (write features through `x_shard`), the partner shards of my column group
+        # are pulled into their global positions, the rest of the buffer is never touched.
+        self.x_full = symm_mem.empty((grid.world * blk, d), dtype=torch.float32, device=dev)
+        self.x_shard = self.x_full[rank * blk:(rank + 1) * blk]
+        self.x_shard.zero_()
+        self.x_shard[:x_local.shape[0]].copy_(x_local)
+        self._hx = symm_mem.rendezvous(self.x_full, group=wgroup)
+        self.recv = symm_mem.empty((pc, blk, d), dtype=torch.float32, device=dev)   # slot k: partial from (j-k) % pc
+        self._hr = symm_mem.rendezvous(self.recv, group=wgroup)
+        self.partial = torch.empty((pc, blk, d), dtype=torch.float32, device=dev)   # my partial sums per row slice
+        self._peer_x = {src: self._hx.get_buffer(src, (grid.world * blk, d), torch.float32)[src * blk:(src + 1) * blk]
+                        for src in grid.col_group_ranks(self.j) if src != rank}
+        self._peer_recv = {r: self._hr.get_buffer(r, (pc, blk, d), torch.float32) for r in grid.row_group_ranks(self.i)}
+        self._copy = torch.cuda.Stream()
+        self._ev_x = torch.cuda.Event()
+        self._ev_slice = [torch.cuda.Event() for _ in range(pc)]
+        self._ev_pushed = torch.cuda.Event()
+        self._tiny = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._scratch = None
+        self._y = torch.empty((self.g1d.n, d), dtype=torch.float32, device=dev)
+        self._skip = [G.heavy_flags(g) if g.n_chunks else None for g in self.slices]
+        self.stage_ms = None            # WDGH_STAGE_TIMES=1: per-stage device times of the last step
+        self._trace = os.environ.get("WDGH_STAGE_TIMES") == "1"
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def _mark(self, marks, name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    def step(self, norm=_lib.NORM_SYM, add_self_loop=True):
+        G, grid = self._G, self.grid
+        part, pc, i, j, r = grid.part, grid.pc, self.i, self.j, self.rank
+        blk = part.block
+        cur = torch.cuda.current_stream()
+        marks = [] if self._trace else None
+        self._mark(marks, "start")
+        labels_full = _all_gather_rows(self.labels_local, self.group)
+        dinv_full = code_full = None
+        if norm != _lib.NORM_NONE:
+            self.g1d._dinv.clear()
+            dinv, _, code = self.g1d.degree_scale(norm, add_self_loop)
+            dinv_full = _all_gather_rows(_pad_rows(dinv, blk), self.group)
+            code_full = _all_gather_rows(_pad_rows(code, blk), self.group) if code is not None else None
+        self._mark(marks, "small all-gathers")
+        # 1. feature shards of my column group: partner shards are pulled, my own is already in place
+        self._copy.wait_stream(cur)
+        with torch.cuda.stream(self._copy):
+            for src, buf in self._peer_x.items():
+                self.x_full[src * blk:(src + 1) * blk].copy_(buf, non_blocking=True)
+            self._ev_x.record(self._copy)
+        # 2. label pass on the 1-D shard, under the pulls
+        self._scratch = G.structure_counts_raw(self.g1d, labels_full, self.c, self._scratch)
+        self._mark(marks, "label pass")
+        cur.wait_event(self._ev_x)
+        self._mark(marks, "wait pulls")
+        # 3. row slices of my block: foreign slices first, each pushed to its owner while the next one is aggregated
+        order = [(j + k) % pc for k in range(1, pc)] + [j]
+        for k, s in enumerate(order, start=1):
+            g = self.slices[s]
+            G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, self.partial[s], norm, add_self_loop,
+                          dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True)
+            self._mark(marks, f"slice {s}")
+            if s != j:
+                self._ev_slice[s].record(cur)
+                owner = i * pc + s
+                with torch.cuda.stream(self._copy):
+                    self._copy.wait_event(self._ev_slice[s])
+                    self._peer_recv[owner][k].copy_(self.partial[s], non_blocking=True)   # slot k at the owner
+        self._ev_pushed.record(self._copy)
+        cur.wait_event(self._ev_pushed)
+        self._mark(marks, "wait pushes")
+        # 4. every rank's pushes have landed once this tiny all-reduce completes (stream-ordered after the pushes)
+        dist.all_reduce(self._tiny, group=self.group)
+        self._mark(marks, "barrier")
+        parts = [self.partial[j]] + [self.recv[k] for k in range(1, pc)]
+        G.reduce_finalize(parts, self.x_full, self._y, norm, add_self_loop, dinv_full, r * blk)
+        self._mark(marks, "reduce + finalize")
+        counters, node_sum = ShardedStats.reduce_counters(self, self._scratch[0], self._scratch[1])
+        if marks is not None:
+            self._mark(marks, "counter all-reduce")
+            torch.cuda.synchronize()
+            self.stage_ms = [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(marks[:-1], marks[1:])]
         return self._y, counters, node_sum
