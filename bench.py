@@ -260,15 +260,10 @@ def main():
                 rp_s, col_s = rowptr, col
             else:
                 rp_s, col_s, _, _ = gen_rows(s0, s1, n, args.avg_degree, C, args.homophily, d, device, want_x=False)
-            keep = grid2.col_in_group(col_s.to(torch.int64), gj)
-            rid = torch.repeat_interleave(torch.arange(s1 - s0, device=device), rp_s[1:] - rp_s[:-1])
-            cnt = torch.bincount(rid[keep], minlength=s1 - s0)
-            rp_f = torch.zeros(s1 - s0 + 1, dtype=torch.int64, device=device)
-            rp_f[1:] = torch.cumsum(cnt, 0)
-            sg = G.CSRGraph(rp_f, col_s[keep].contiguous(), None, s1 - s0, row_offset=s0, n_global=n)
+            rp_f, col_f = grid2.filter_slice(rp_s, col_s, gj)
+            sg = G.CSRGraph(rp_f, col_f, None, s1 - s0, row_offset=s0, n_global=n)
             _ = sg.plan
             slice_graphs.append(sg)
-            del keep, rid, cnt
         torch.cuda.empty_cache()
     nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device=device)
     if world > 1:

@@ -147,3 +147,66 @@ def test_world2_step_matches_single_process_oracle():
         keep = s["deg_nsl"] > 0
         ref_sum = (s["match_nsl"][keep].astype(np.float32) / s["deg_nsl"][keep].astype(np.float32)).astype(np.float64).sum()
         assert abs(r[5] - ref_sum) < 1e-9
+
+
+def _worker_2d(rank, world, port, out):
+    """One rank of the 2-D partition on CPU: Grid2D's slicing + schedule (product code) drive a gloo exchange."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wdgh_b200.sharded import Grid2D, shard_csr
+
+        row, col, labels, x = _graph()
+        n, d = labels.shape[0], x.shape[1]
+        grid = Grid2D(n, world, 2)
+        blk, pc = grid.part.block, grid.pc
+        i, j = grid.coords(rank)
+        rowptr = O.csr_from_coo(row, n)
+        deg = np.diff(rowptr).astype(np.float64) + 1.0
+        dinv = (1.0 / np.sqrt(deg)).astype(np.float32)
+        # features of my column group only (what the pulls deliver); everything else stays NaN on purpose
+        x_cols = np.full((world * blk, d), np.nan, np.float32)
+        for src in grid.col_group_ranks(j):
+            a, b = grid.part.bounds(src)
+            x_cols[a:b] = x[a:b]
+        partial, sends = {}, []
+        for k, s, owner in grid.schedule(rank):
+            r0, r1 = grid.part.bounds(owner)
+            lrp, lcol, _ = shard_csr(rowptr, col, None, r0, r1)
+            frp, fcol = grid.filter_slice(torch.from_numpy(lrp), torch.from_numpy(lcol), j)
+            frp, fcol = frp.numpy(), fcol.numpy()
+            p = np.zeros((blk, d), np.float32)
+            np.add.at(p, np.repeat(np.arange(r1 - r0), np.diff(frp)), dinv[fcol][:, None] * x_cols[fcol])
+            assert np.isfinite(p).all()
+            partial[s] = p
+            if owner != rank:
+                sends.append(dist.isend(torch.from_numpy(p), dst=owner, tag=k))
+        recv = [torch.empty((blk, d)) for _ in range(pc)]
+        reqs = [dist.irecv(recv[k], src=grid.slot_source(rank, k), tag=k) for k in range(1, pc)]
+        [q.wait() for q in reqs + sends]
+        r0, r1 = grid.part.bounds(rank)
+        acc = partial[j].copy()
+        for k in range(1, pc):
+            acc += recv[k].numpy()
+        y = (acc[:r1 - r0] + dinv[r0:r1, None] * x[r0:r1]) * dinv[r0:r1, None]
+        out.put((rank, y))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world4_2d_partition_matches_single_process_oracle():
+    world = 4
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_2d, args=(r, world, port, out)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([out.get(timeout=150) for _ in range(world)], key=lambda t: t[0])
+    [p.join(30) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    row, col, labels, x = _graph()
+    n = labels.shape[0]
+    r2, c2, v2 = O.sys_normalized_adjacency(row, col, np.ones(row.shape[0], np.float32), n)
+    ref_y = O.spmm(r2, c2, v2, n, x)
+    np.testing.assert_allclose(np.concatenate([r[1] for r in res]), ref_y, rtol=1e-5, atol=1e-6)

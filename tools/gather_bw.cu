@@ -111,6 +111,46 @@ __global__ void gather_cpasync(const float4 *__restrict__ x, const int *__restri
   if (acc.x == 12345.678f) out[warp * 32 + lane] = acc;
 }
 
+// gathers + one 512-byte output row per K gathers (the SpMM's read/write mix at full memory-level parallelism:
+// batches of U are cut from the entry stream of 32 consecutive output rows, whatever K is).
+// STORE: 0 = st.global, 1 = st.global.cs (streaming), 2 = no store (the K-row sums are discarded)
+template <int U, int STORE>
+__global__ void gather_write(const float4 *__restrict__ x, const int *__restrict__ idx, long rows, int K, float4 *y) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long groups = rows / 32;
+  float4 acc = make_float4(0, 0, 0, 0);
+  float4 sink = make_float4(0, 0, 0, 0);
+  for (long g = warp; g < groups; g += nwarps) {
+    const long e0 = g * 32 * K, total = 32L * K;
+    long row = g * 32;
+    int in_row = 0;
+    for (long t0 = 0; t0 < total; t0 += 32) {
+      const int j = idx[e0 + t0 + lane];
+      for (int k = 0; k < 32; k += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_na(x + (long)__shfl_sync(0xffffffffu, j, k + u) * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          if (++in_row == K) {
+            float4 *dst = y + row * 32 + lane;
+            if (STORE == 0) *dst = acc;
+            else if (STORE == 1) asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+            else { sink.x += acc.x; }
+            acc = make_float4(0, 0, 0, 0);
+            in_row = 0;
+            ++row;
+          }
+        }
+      }
+    }
+  }
+  if (sink.x == 12345.678f) y[lane] = sink;
+}
+
 template <typename F>
 static float time_ms(F f, int reps) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -125,6 +165,7 @@ static float time_ms(F f, int reps) {
 int main(int argc, char **argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 16000000;   // rows of 512 B
   const long m = argc > 2 ? atol(argv[2]) : 256000000; // gathers
+  const bool rw_only = argc > 3;                       // any third argument: only the read/write-mix cases
   float4 *x, *out; int *idx;
   CK(cudaMalloc(&x, (size_t)n * 512)); CK(cudaMemset(x, 0, (size_t)n * 512));
   CK(cudaMalloc(&out, 1 << 24)); CK(cudaMalloc(&idx, m * 4 + 4096));
@@ -134,6 +175,24 @@ int main(int argc, char **argv) {
   printf("rows=%d (%.1f GB) gathers=%ld sms=%d\n", n, n * 512.0 / 1e9, m, sms);
 #define RUN_REG(U, BLOCK, PER_SM) { float ms = time_ms([&] { gather_reg<U><<<sms * PER_SM, BLOCK>>>(x, idx, m, out); }, 3); \
     CK(cudaGetLastError()); printf("reg  U=%2d block=%3d ctas/sm=%2d : %7.2f ms %7.1f GB/s\n", U, BLOCK, PER_SM, ms, bytes / ms / 1e6); }
+  {
+    // read/write mix: K gathers per 512 B output row (K = 20: the 1-D shard, K = 5: a row slice of the 2-D partition)
+    float4 *y;
+    const int Ks[3] = {20, 5, 2};
+    CK(cudaMalloc(&y, (size_t)(m / 2) * 512 + 4096));
+    for (int K : Ks) {
+      const long rows = (m / K) / 32 * 32;
+      const double rd = (double)rows * K * 516, wr = (double)rows * 512;
+      float ms = time_ms([&] { gather_write<8, 2><<<sms * 32, 32>>>(x, idx, rows, K, y); }, 3);
+      printf("K=%2d gathers/row, no store      : %7.2f ms %7.1f GB/s\n", K, ms, rd / ms / 1e6);
+      ms = time_ms([&] { gather_write<8, 0><<<sms * 32, 32>>>(x, idx, rows, K, y); }, 3);
+      printf("K=%2d gathers/row, st.global     : %7.2f ms %7.1f GB/s (reads + writes)\n", K, ms, (rd + wr) / ms / 1e6);
+      ms = time_ms([&] { gather_write<8, 1><<<sms * 32, 32>>>(x, idx, rows, K, y); }, 3);
+      printf("K=%2d gathers/row, st.global.cs  : %7.2f ms %7.1f GB/s (reads + writes)\n", K, ms, (rd + wr) / ms / 1e6);
+    }
+    CK(cudaFree(y));
+    if (rw_only) return 0;
+  }
   RUN_REG(8, 32, 32) RUN_REG(8, 128, 8) RUN_REG(16, 32, 20) RUN_REG(16, 32, 32) RUN_REG(4, 32, 32) RUN_REG(32, 32, 16)
   {
     float *sc4; unsigned char *sc1; float *table;

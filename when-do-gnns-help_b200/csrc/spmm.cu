@@ -478,6 +478,260 @@ spmm_rows_pipelined_kernel(const int64_t *__restrict__ rowptr, const int32_t *__
 }
 
 // ---------------------------------------------------------------------------
+// Row-group kernel: the persistent one-warp CTA walks GROUPS of 32 consecutive rows and treats the stored
+// entries of a group as one stream.  The gather batches (U feature rows in flight per lane) are cut from the
+// stream, not from a row, so short rows no longer mean short batches: a row of 3 entries shares its batch
+// with its neighbours, every batch but the last of a group is full and unpredicated.  Row boundaries are
+// found on the consuming side (each entry carries its row slot; a change flushes the accumulator).
+//   * lane l owns row 32 g + l of the group: bounds, D^-1/2 scale and skip flag are one coalesced load each;
+//   * an inclusive warp scan of the row lengths gives the stream offsets (shared memory, double buffered so
+//     that the next group's first segment is requested while the current group's last batch is in flight);
+//   * each lane finds the row of its stream position with a 5-step search in the offsets;
+//   * the self loop is a virtual LAST entry of its row (column = the row itself, weight = s_i): its feature
+//     row rides in the gather batches instead of being fetched after them, and the summation order -- stored
+//     entries in CSR order, then the self loop -- is the one of the row kernels, so results are bit-identical.
+// Split ("heavy") rows contribute no entries and are not stored; the chunk kernels own them.
+// ---------------------------------------------------------------------------
+template <int VEC, int NCH, bool HAS_VAL, bool FULL, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                     const float *__restrict__ val, int64_t n, const float *__restrict__ x, int d, int64_t ldx,
+                     float *__restrict__ y, int64_t ldy, int norm, int self_loop,
+                     const float *__restrict__ dinv, const uint8_t *__restrict__ deg_code, int64_t threshold,
+                     int64_t row_offset, RangeArgs ra, unsigned long long *__restrict__ next_group) {
+  constexpr int TILE = 32 * VEC * NCH;
+  constexpr int U0 = 32 / (VEC * NCH);
+  constexpr int U = U0 > 16 ? 16 : (U0 < 2 ? 2 : U0);
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ float table[256];
+  __shared__ int s_off[2][33];      // stream offset of every row slot of the group (exclusive scan), [32] = total
+  __shared__ int64_t s_beg[2][32];  // first stored entry of every row slot
+  const int lane = threadIdx.x;
+  const bool sym = (norm == WDGH_NORM_SYM);
+  const bool coded = sym && deg_code != nullptr;
+  const bool virt = self_loop && ra.finalize;  // self loop = virtual trailing entry of its row
+  if (coded) {
+    for (int c = lane; c < 256; c += 32) {
+      double rs = (double)c + (self_loop ? 1.0 : 0.0);
+      if (rs == 0.0) rs = 1.0;
+      table[c] = (float)(1.0 / sqrt(rs));  // same expression as degree_scale_kernel -> same bits
+    }
+    __syncwarp();
+  }
+  const int cbase = FULL ? 0 : blockIdx.y * TILE;
+  bool live[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) live[t] = FULL || (cbase + (t * 32 + lane) * VEC < d);
+  const int64_t W = gridDim.x;
+  const int64_t n_groups = (n + 31) >> 5;
+  const int ld32 = (int)ldx;
+  const float *xl = x + cbase + lane * VEC;
+
+  auto load_bounds = [&](int64_t g, int64_t &b, int64_t &e, int &flag) {
+    b = 0;
+    e = 0;
+    flag = 0;
+    const int64_t r = (g << 5) + lane;
+    if (r < n) {
+      b = __ldg(rowptr + r);
+      e = ra.row_end ? __ldg(ra.row_end + r) : __ldg(rowptr + r + 1);
+      if (ra.skip) flag = __ldg(ra.skip + r);
+    }
+  };
+  // scan the row lengths of group g into s_off[buf] / s_beg[buf]
+  auto publish = [&](int buf, int64_t g, int64_t b, int64_t e, int flag, unsigned &nostore, int &total, float &si) {
+    const int64_t r = (g << 5) + lane;
+    const bool inr = r < n;
+    const bool hv = inr && (flag != 0 || e - b > threshold);
+    int inc = (!inr || hv) ? 0 : (int)(e - b) + (virt ? 1 : 0);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
+    }
+    s_off[buf][lane + 1] = inc;
+    if (lane == 0) s_off[buf][0] = 0;
+    s_beg[buf][lane] = b;
+    nostore = __ballot_sync(kFull, !inr || hv);
+    total = __shfl_sync(kFull, inc, 31);
+    si = (norm != WDGH_NORM_NONE && ra.finalize && inr) ? __ldg(dinv + r + row_offset) : 1.f;
+    __syncwarp();
+  };
+  // column id, weight and row slot of stream position t0 + lane of group g
+  auto load_seg = [&](int buf, int64_t g, int t0, int total, int &j, float &w, int &rho) {
+    j = 0;
+    w = 0.f;
+    rho = 0;
+    const int t = t0 + lane;
+    if (t < total) {
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1)
+        if (s_off[buf][lo + step] <= t) lo += step;
+      rho = lo;
+      const int k = t - s_off[buf][lo];
+      if (virt && k == s_off[buf][lo + 1] - s_off[buf][lo] - 1) {
+        const int64_t grow = (g << 5) + lo + row_offset;
+        j = (int)grow;
+        w = sym ? __ldg(dinv + grow) : 1.f;
+      } else {
+        const int64_t idx = s_beg[buf][lo] + k;
+        j = __ldg(col + idx);
+        w = HAS_VAL ? __ldg(val + idx) : 1.f;
+        if (coded) {
+          const int c = __ldg(deg_code + j);
+          w *= (c < 255) ? table[c] : __ldg(dinv + j);
+        } else if (sym) {
+          w *= __ldg(dinv + j);
+        }
+      }
+    }
+  };
+
+  // group order: static stride W, or (next_group != nullptr) a ticket counter -- row lengths are heavy-tailed,
+  // with tickets a warp that drew long rows simply takes fewer groups
+  auto take = [&](int64_t prev) -> int64_t {
+    if (next_group == nullptr || !FULL) return prev + W;
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(next_group, 1ull);
+    return (int64_t)__shfl_sync(kFull, t, 0) + W;  // tickets start after the W groups handed out by blockIdx
+  };
+  int64_t g = blockIdx.x;
+  if (g >= n_groups) return;
+  int64_t b, e;
+  int flag;
+  load_bounds(g, b, e, flag);
+  int buf = 0;
+  unsigned nostore, n_nostore = kFull;
+  int total, n_total = 0;
+  float si_l, n_si = 1.f;
+  publish(0, g, b, e, flag, nostore, total, si_l);
+  int64_t gn = take(g);
+  int64_t gnn = 0;
+  load_bounds(gn, b, e, flag);  // the next group's bounds travel while this group is aggregated
+  int j, rho, nj = 0, nrho = 0;
+  float w, nw = 0.f;
+  load_seg(0, g, 0, total, j, w, rho);
+  Vec<VEC> acc[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) acc[t].zero();
+
+  // store row slot `cur` of the current group (accumulator -> y) and clear the accumulator
+  auto flush_row = [&](int cur) {
+    if (!((nostore >> cur) & 1u)) {
+      const int64_t row = (g << 5) + cur;
+      const float si = __shfl_sync(kFull, si_l, cur);
+      const bool had = s_off[buf][cur + 1] != s_off[buf][cur];
+      if (had || ra.finalize || !ra.accumulate) {  // an empty range adds nothing to an earlier phase's sum
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+          if (live[t]) {
+            const int c = cbase + (t * 32 + lane) * VEC;
+            if (ra.accumulate) {
+              Vec<VEC> prev;
+              prev.load_plain(y + row * ldy + c);
+              acc[t].add(prev);
+            }
+            if (ra.finalize) {
+              acc[t].scale(si);
+              acc[t].store_stream(y + row * ldy + c);
+            } else {
+              acc[t].store(y + row * ldy + c);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) acc[t].zero();
+  };
+
+  while (true) {
+    int cur = 0;
+    bool next_ready = false;
+    auto prefetch = [&](int t0, bool last_seg) {
+      if (!last_seg) {
+        load_seg(buf, g, t0 + 32, total, nj, nw, nrho);
+      } else {  // next group: offsets, first segment, and the bounds of the group after it
+        publish(buf ^ 1, gn, b, e, flag, n_nostore, n_total, n_si);
+        load_seg(buf ^ 1, gn, 0, n_total, nj, nw, nrho);
+        gnn = take(gn);
+        load_bounds(gnn, b, e, flag);
+        next_ready = true;
+      }
+    };
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int cnt = min(32, total - t0);
+      const bool last_seg = t0 + 32 >= total;
+      bool next_issued = false;
+      int k = 0;
+      for (; k + U <= cnt; k += U) {  // full batches: U unpredicated gathers in flight
+        Vec<VEC> v[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, k + u) * ld32;
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) {
+            if (live[t]) v[u][t].load(xr + t * (32 * VEC));
+            else v[u][t].zero();
+          }
+        }
+        if (!next_issued) {
+          prefetch(t0, last_seg);
+          next_issued = true;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int ru = __shfl_sync(kFull, rho, k + u);
+          while (cur < ru) flush_row(cur++);
+          const float wu = __shfl_sync(kFull, w, k + u);
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) acc[t].fma(wu, v[u][t]);
+        }
+      }
+      if (k < cnt) {  // last batch of the group, predicated
+        Vec<VEC> v[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool on = k + u < cnt;
+          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, on ? k + u : 0) * ld32;
+#pragma unroll
+          for (int t = 0; t < NCH; ++t) {
+            if (on && live[t]) v[u][t].load(xr + t * (32 * VEC));
+            else v[u][t].zero();
+          }
+        }
+        if (!next_issued) {
+          prefetch(t0, last_seg);
+          next_issued = true;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (k + u < cnt) {
+            const int ru = __shfl_sync(kFull, rho, k + u);
+            while (cur < ru) flush_row(cur++);
+            const float wu = __shfl_sync(kFull, w, k + u);
+#pragma unroll
+            for (int t = 0; t < NCH; ++t) acc[t].fma(wu, v[u][t]);
+          }
+        }
+      }
+      j = nj; w = nw; rho = nrho;
+    }
+    if (!next_ready) {  // a group without entries
+      prefetch(0, true);
+      j = nj; w = nw; rho = nrho;
+    }
+    while (cur < 32) flush_row(cur++);
+    g = gn;
+    gn = gnn;
+    buf ^= 1;
+    nostore = n_nostore; total = n_total; si_l = n_si;
+    if (g >= n_groups) break;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // nnz-balanced streaming kernel (d % 4 == 0, d >= 128): one warp per UNIT of WDGH_UNIT consecutive
 // stored entries, whatever rows they belong to.  Every warp always has full 32-entry segments and
 // U gathers in flight, a hub row is just many units, and short rows cost no idle lanes -- this is
@@ -785,8 +1039,60 @@ static int pipelined_minb() {
   return cached;
 }
 
+// WDGH_ROWGROUP: 2 (default) = row-group kernel, groups handed out by a ticket counter; 1 = row-group kernel,
+// static stride; 0 = the per-row pipelined kernel.  Measured on rows [0, 6.25M) of the 50M-node bench graph, d=128:
+//   full rows (19.5 entries/row):      0 -> 11.34 ms, 1 -> 11.62 ms, 2 -> 10.73 ms
+//   one 2-D row slice (4.9 entries/row): 0 -> 3.98 ms, 1 -> 3.87 ms, 2 -> 3.63 ms
+static int rowgroup_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char *e = getenv("WDGH_ROWGROUP");
+    cached = e ? atoi(e) : 2;
+    if (cached < 0 || cached > 2) cached = 2;
+  }
+  return cached;
+}
+// ticket counters of the row-group kernel: one slot per launch, 64 launches may be in flight
+static unsigned long long *ticket_slot(cudaStream_t st) {
+  static unsigned long long *ring = nullptr;
+  static unsigned next = 0;
+  if (!ring && cudaMalloc(&ring, 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  unsigned long long *slot = ring + (next++ & 63u);
+  if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
+  return slot;
+}
+
+template <int VEC, int NCH, bool HAS_VAL>
+static int launch_rowgroup(const SpmmArgs &a) {
+  constexpr int TILE = 32 * VEC * NCH;
+  const int minb = (NCH == 1) ? pipelined_minb() : 16;
+  const int64_t n_groups = (a.n + 31) / 32;
+  int64_t ctas = (int64_t)sm_count() * minb;
+  if (ctas > n_groups) ctas = n_groups;
+  dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, TILE));
+  const bool full = (a.d == TILE);
+  unsigned long long *tickets = (rowgroup_enabled() == 2 && full) ? ticket_slot(a.st) : nullptr;
+#define WDGH_RG_LAUNCH(FULLV, MINB)                                                                                \
+  spmm_rowgroup_kernel<VEC, NCH, HAS_VAL, FULLV, MINB><<<grid, 32, 0, a.st>>>(                                       \
+      a.rowptr, a.col, a.val, a.n, a.x, a.d, a.ldx, a.y, a.ldy, a.norm, a.self_loop, a.dinv, a.deg_code, a.threshold, \
+      a.row_offset, a.ra, tickets)
+  if (full) {
+    switch (minb) {
+      case 32: WDGH_RG_LAUNCH(true, 32); break;
+      case 24: WDGH_RG_LAUNCH(true, 24); break;
+      default: WDGH_RG_LAUNCH(true, 16); break;
+    }
+  } else {
+    WDGH_RG_LAUNCH(false, 16);
+  }
+#undef WDGH_RG_LAUNCH
+  WDGH_LAUNCHED("spmm_rowgroup_kernel");
+  return 0;
+}
+
 template <int VEC, int NCH, bool HAS_VAL>
 static int launch_pipelined(const SpmmArgs &a) {
+  if (!a.stats && rowgroup_enabled()) return launch_rowgroup<VEC, NCH, HAS_VAL>(a);
   constexpr int TILE = 32 * VEC * NCH;
   const int minb = (NCH == 1) ? pipelined_minb() : 16;
   int64_t ctas = (int64_t)sm_count() * minb;

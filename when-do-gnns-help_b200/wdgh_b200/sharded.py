@@ -312,6 +312,28 @@ class Grid2D:
         """Boolean mask: which column ids belong to column group j."""
         return (col // max(self.part.block, 1)) % self.pc == j
 
+    def filter_slice(self, rowptr, col, j: int):
+        """CSR (torch tensors, any device) of one rank's rows -> the same rows restricted to column group j."""
+        rows = int(rowptr.shape[0]) - 1
+        keep = self.col_in_group(col.to(torch.int64), j)
+        rid = torch.repeat_interleave(torch.arange(rows, device=col.device), rowptr[1:] - rowptr[:-1])
+        out = torch.zeros(rows + 1, dtype=torch.int64, device=col.device)
+        out[1:] = torch.cumsum(torch.bincount(rid[keep], minlength=rows), 0)
+        return out, col[keep].contiguous()
+
+    def schedule(self, rank: int):
+        """Order in which `rank` aggregates the row slices of its block: [(k, s, owner)], k = 1 .. pc.
+
+        Foreign slices first (slice s = (j + k) % pc is sent to its owner (i, s) and lands in the owner's
+        receive slot k), the rank's own slice (k = pc, nothing to send) last."""
+        i, j = self.coords(rank)
+        return [(k, (j + k) % self.pc, i * self.pc + (j + k) % self.pc) for k in range(1, self.pc + 1)]
+
+    def slot_source(self, rank: int, k: int) -> int:
+        """Rank whose partial sums arrive in receive slot k (1 <= k < pc) of `rank`."""
+        i, j = self.coords(rank)
+        return i * self.pc + (j - k) % self.pc
+
 
 class Cuda2DShardedStats:
     """A_hat X on the 2-D partition + label statistics on the 1-D row shard (see Grid2D).
@@ -358,6 +380,9 @@ class Cuda2DShardedStats:
         self._skip = [G.heavy_flags(g) if g.n_chunks else None for g in self.slices]
         self.stage_ms = None            # WDGH_STAGE_TIMES=1: per-stage device times of the last step
         self._trace = os.environ.get("WDGH_STAGE_TIMES") == "1"
+        # WDGH_2D_DIRECT=1: the aggregation kernel stores foreign row slices straight into the owner's receive
+        # buffer over NVLink (no local partial buffer, no copy-engine push)
+        self._direct = os.environ.get("WDGH_2D_DIRECT", "0") == "1"
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -394,15 +419,15 @@ class Cuda2DShardedStats:
         cur.wait_event(self._ev_x)
         self._mark(marks, "wait pulls")
         # 3. row slices of my block: foreign slices first, each pushed to its owner while the next one is aggregated
-        order = [(j + k) % pc for k in range(1, pc)] + [j]
-        for k, s in enumerate(order, start=1):
+        for k, s, owner in grid.schedule(r):
             g = self.slices[s]
-            G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, self.partial[s], norm, add_self_loop,
+            direct = self._direct and s != j
+            out = self._peer_recv[owner][k] if direct else self.partial[s]
+            G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, out, norm, add_self_loop,
                           dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True)
             self._mark(marks, f"slice {s}")
-            if s != j:
+            if s != j and not direct:
                 self._ev_slice[s].record(cur)
-                owner = i * pc + s
                 with torch.cuda.stream(self._copy):
                     self._copy.wait_event(self._ev_slice[s])
                     self._peer_recv[owner][k].copy_(self.partial[s], non_blocking=True)   # slot k at the owner
