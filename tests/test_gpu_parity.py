@@ -284,6 +284,45 @@ def test_spmm_on_the_fly_norm_vs_oracle(W, norm, self_loop):
     np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 95, 1000])
+@pytest.mark.parametrize("d", [32, 64, 128, 200, 256])
+def test_spmm_row_group_boundaries(W, n, d):
+    """The row-group kernel walks groups of 32 rows: sizes around the group width, rows without entries (whole
+    empty groups included), a split row next to empty ones, with and without values / self loop / normaliser."""
+    rng = np.random.default_rng(n * 1000 + d)
+    deg = rng.integers(0, 7, n)
+    deg[rng.random(n) < 0.4] = 0              # many empty rows
+    if n >= 64:
+        deg[32:64] = 0                        # one group without any stored entry
+    if n > 40:
+        deg[n // 2] = min(n, 600)             # a split row (threshold 32 below)
+    src = np.repeat(np.arange(n), deg)
+    dst = rng.integers(0, n, src.shape[0])
+    row, col, _ = O.coalesce(src, dst, None, n)
+    keep = row != col
+    row, col = row[keep], col[keep]
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    xt = torch.from_numpy(x)
+    ei = torch.from_numpy(np.vstack([row, col]).astype(np.int64)).reshape(2, -1)
+    ones = np.ones(row.shape[0], np.float32)
+    # binary adjacency, D^-1/2 (A+I) D^-1/2 and D^-1 (A+I) on the fly
+    g = W.CSRGraph.from_coo_indices(ei, None, n, threshold=32)
+    assert n <= 40 or g.n_heavy >= 1
+    for norm, fn in ((2, O.sys_normalized_adjacency), (1, O.row_normalized_adjacency)):
+        y = W.spmm(g, xt, norm, True).cpu().numpy()
+        r, c, v = fn(row, col, ones, n)
+        ref = O.spmm(r, c, v, n, x)
+        np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * max(np.abs(ref).max(), 1e-30))
+    # plain A X (no self loop: rows without entries must come back as exact zeros) with explicit values
+    val = (rng.random(row.shape[0]) + 0.5).astype(np.float32)
+    gv = W.CSRGraph.from_coo_indices(ei, torch.from_numpy(val), n, threshold=32)
+    y = W.spmm(gv, xt).cpu().numpy()
+    ref = O.spmm(row, col, val, n, x)
+    np.testing.assert_allclose(y, ref, rtol=RTOL, atol=1e-5 * max(np.abs(ref).max(), 1e-30))
+    empty = np.bincount(row, minlength=n) == 0
+    assert not y[empty].any()
+
+
 @pytest.mark.parametrize("c,avg", [(2, 3), (7, 9), (10, 20), (40, 40), (70, 5)])
 def test_structure_counts_vs_oracle(W, c, avg):
     n = 20000
