@@ -317,7 +317,7 @@ def main():
     ms = float(ms_t.item())
     value = nnz / (ms * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (spmm_rows_kernel), timed alone on this rank's shard -------
+    # ---- roofline of the dominant kernel (spmm_rowgroup_kernel), timed alone on this rank's shard ----
     if world == 1:
         xs = x_local
         dinv, _, code = g.degree_scale(W.NORM_SYM, True)
@@ -378,7 +378,7 @@ def main():
         traffic = traffic * nnz_local if traffic is not None else None
     except Exception:
         pass
-    roofline = {"kernel": "spmm_rows_pipelined_kernel<1,0,1,32> (+ chunk kernels for split rows)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "spmm_rowgroup_kernel<VEC=4,NCH=1,binary,FULL,32 CTAs/SM> (+ spmm_chunks / spmm_heavy_finish for split rows)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": spmm_ms, "algorithmic_bytes": alg_bytes, "share_of_step": spmm_ms / ms}
 

@@ -40,6 +40,9 @@ extern "C" {
 #define WDGH_NORM_NONE 0 /* Y = A X                       (torch.spmm(adj, x), hm.py:192,199,234)          */
 #define WDGH_NORM_RW   1 /* Y = D^-1 (A [+I]) X           (row_normalized_adjacency, util_funcs.py:383-390) */
 #define WDGH_NORM_SYM  2 /* Y = D^-1/2 (A [+I]) D^-1/2 X  (sys_normalized_adjacency, util_funcs.py:418-426) */
+/* scale modes of wdgh_degree_scale / wdgh_scale_values only (the other util_funcs.py normalisers; not valid for the SpMM) */
+#define WDGH_NORM_RW_SUM  3 /* r_i = 1 / rowsum_i (signed sum), inf -> 0   (normalize :29-36, preprocess_features :39-46) */
+#define WDGH_NORM_SYM_RAW 4 /* r_i = rowsum_i^-1/2, inf -> 0, no 0 -> 1 substitution       (normalize_adj :429-436)    */
 
 /* ---- library ------------------------------------------------------------ */
 int         wdgh_version(void);

@@ -36,7 +36,8 @@ import torch
 
 __all__ = [
     "coalesce", "csr_from_coo", "sys_normalized_adjacency", "row_normalized_adjacency",
-    "normalize_tensor", "spmm", "structure_counts", "edge_homophily", "node_homophily",
+    "normalize_tensor", "normalize", "preprocess_features", "normalize_adj",
+    "dataset_edge_balance", "spmm", "structure_counts", "edge_homophily", "node_homophily",
     "compat_matrix", "class_homophily", "class_distribution", "adjusted_homo",
     "label_informativeness", "edge_cosine", "generalized_edge_homophily", "similarity",
     "gntk_kernels", "random_disassortative_splits", "accuracy", "kr_metric",
@@ -110,6 +111,63 @@ def normalize_tensor(mx, symmetric=0):
     r = rowsum.pow(-0.5).flatten()
     r[torch.isinf(r)] = 0.0
     return (r[:, None] * mx) * r[None, :]         # diag(r) @ mx @ diag(r)
+
+
+def normalize(mx):
+    """Row-normalise a matrix: diag(1 / rowsum) @ mx, rows with a zero sum stay zero.  util_funcs.py:29-36.
+    (`preprocess_features`, util_funcs.py:39-46, is the same arithmetic applied to the feature matrix.)
+
+    Dense input (numpy / torch, the synthetic_plot.py:82,92 flow) -> dense numpy array of the input's dtype;
+    scipy sparse input (the full_load_data flow) -> scipy CSR in the dtype scipy promotes to."""
+    if sp.issparse(mx):
+        rowsum = np.asarray(mx.sum(1))
+        with np.errstate(divide="ignore"):
+            r_inv = (1 / rowsum).flatten()
+        r_inv[np.isinf(r_inv)] = 0.0
+        return sp.diags(r_inv).dot(mx)
+    if isinstance(mx, torch.Tensor):               # the row sum is torch's (its float32 summation order), :31
+        m, rowsum = mx.detach().cpu().numpy(), mx.detach().cpu().sum(1).numpy()
+    else:
+        m = np.asarray(mx)
+        rowsum = m.sum(1)
+    with np.errstate(divide="ignore"):
+        r_inv = (1 / rowsum).flatten()
+    r_inv[np.isinf(r_inv)] = 0.0
+    return sp.diags(r_inv).dot(m)
+
+
+preprocess_features = normalize
+
+
+def normalize_adj(row, col, val, n):
+    """(A D^-1/2)^T D^-1/2 = D^-1/2 A^T D^-1/2 with D = diag(row sums of A), float64.  util_funcs.py:429-436.
+    Returns the coalesced COO triple of the result (values float64)."""
+    a = sp.coo_matrix((np.asarray(val, dtype=np.float64), (row, col)), shape=(n, n))
+    rowsum = np.asarray(a.sum(1))
+    with np.errstate(divide="ignore"):
+        dis = np.power(rowsum, -0.5).flatten()
+    dis[np.isinf(dis)] = 0.0
+    d = sp.diags(dis)
+    m = a.dot(d).transpose().dot(d).tocoo()
+    key = m.row.astype(np.int64) * n + m.col
+    order = np.argsort(key, kind="stable")
+    return m.row[order].astype(np.int64), m.col[order].astype(np.int64), m.data[order]
+
+
+def dataset_edge_balance(row, col, val, labels, n):
+    """Per class: node count, adjacency mass inside the class, adjacency mass leaving it.  util_funcs.py:439-451."""
+    labels = np.asarray(labels)
+    c = int(labels.max()) + 1
+    a = sp.coo_matrix((np.asarray(val, dtype=np.float64), (row, col)), shape=(n, n)).tocsr()
+    nodes = np.zeros(c)
+    balance = np.zeros((c, 2))
+    for i in range(c):
+        idx = np.where(labels == i)[0]
+        rest = np.delete(np.arange(n), idx)
+        nodes[i] = idx.shape[0]
+        balance[i, 0] = a[idx, :][:, idx].sum()
+        balance[i, 1] = a[idx, :][:, rest].sum()
+    return nodes, balance
 
 
 def spmm(row, col, val, n, x, threads=None):

@@ -366,9 +366,50 @@ def case_plot_variants():
         save(f"plot_syn_{nedge}_{h}_{s}", **out)
 
 
+# --------------------------------------------------------------------------
+# case 5: the remaining normalisers / edge statistics of util_funcs.py that sit next to the path
+# (normalize :29, preprocess_features :39, normalize_adj :429, dataset_edge_balance :439)
+# --------------------------------------------------------------------------
+def case_util_norm():
+    rng = np.random.default_rng(2024)
+    n, c = 350, 5
+    r, q = rng.integers(0, n - 6, 2600), rng.integers(0, n - 6, 2600)      # directed, last 6 rows/cols empty
+    vals = (rng.random(2600) + 0.25).astype(np.float64)
+    a = sp.coo_matrix((vals, (r, q)), shape=(n, n)).tocsr()                # duplicates summed
+    a.sort_indices()
+    coo = a.tocoo()
+    labels = rng.integers(0, c, n)
+    labels[:c] = np.arange(c)
+    feats = sp.random(n, 40, density=0.15, random_state=7, format="csr", dtype=np.float64)
+    feats.data = np.ceil(feats.data * 4)                                   # bag-of-words like counts, some empty rows
+    out = {"in_n": np.int64(n), "in_row": coo.row.astype(np.int32), "in_col": coo.col.astype(np.int32),
+           "in_val": coo.data.astype(np.float64), "in_labels": labels.astype(np.int64)}
+    fc = feats.tocoo()
+    out["in_feat_row"], out["in_feat_col"], out["in_feat_val"] = fc.row.astype(np.int32), fc.col.astype(np.int32), fc.data
+    out["in_feat_dim"] = np.int64(40)
+    # scipy-sparse flow (full_load_data: util_funcs.py:189-190)
+    m = sp.csr_matrix(uf.normalize(a)); m.sort_indices()
+    out["out_normalize_indptr"], out["out_normalize_indices"], out["out_normalize_data"] = m.indptr, m.indices, m.data
+    f = sp.csr_matrix(uf.preprocess_features(feats)); f.sort_indices()
+    out["out_preprocess_indptr"], out["out_preprocess_indices"], out["out_preprocess_data"] = f.indptr, f.indices, f.data
+    # dense torch flow (synthetic_plot.py:82,92)
+    dense = torch.from_numpy(a.toarray()).float()
+    out["out_normalize_dense"] = np.asarray(uf.normalize(dense + torch.eye(n)))
+    out["out_preprocess_dense"] = np.asarray(uf.preprocess_features(torch.from_numpy(feats.toarray()).float()))
+    na = uf.normalize_adj(a).tocsr(); na.sort_indices()
+    out["out_normalize_adj_indptr"], out["out_normalize_adj_indices"], out["out_normalize_adj_data"] = (
+        na.indptr, na.indices, na.data)
+    nodes, bal = uf.dataset_edge_balance(a.toarray(), torch.from_numpy(labels))
+    out["out_balance_nodes"], out["out_balance"] = nodes, bal
+    b = (a != 0).astype(np.float64)
+    nodes_b, bal_b = uf.dataset_edge_balance(b.toarray(), torch.from_numpy(labels))
+    out["out_balance_binary"] = bal_b
+    save("util_norm", **out)
+
+
 if __name__ == "__main__":
-    case_plot_variants()
-    case_cora()
-    case_synthetic()
-    case_edge_cases()
+    cases = {"plot": case_plot_variants, "cora": case_cora, "synthetic": case_synthetic, "edge": case_edge_cases,
+             "util_norm": case_util_norm}
+    for name in (sys.argv[1:] or list(cases)):     # no argument = regenerate everything
+        cases[name]()
     os.chdir(_cwd)

@@ -702,3 +702,40 @@ def test_pipeline_host_entry(W, d, chunks_note):
     assert abs(node_sum[0] - s.node_sum) <= 1e-9 * max(1.0, s.node_sum)
     o = O.structure_counts(row, col, labels.astype(np.int64), n, num_classes=c)
     assert np.array_equal(s.hist, o["hist"])
+
+
+# ---------------------------------------------------------------------------
+# util_funcs.py normalisers next to the path (normalize, preprocess_features, normalize_adj, dataset_edge_balance)
+# against the reference's golden outputs (tests/golden/util_norm.npz)
+# ---------------------------------------------------------------------------
+def test_util_normalisers_golden(W):
+    import scipy.sparse as sp
+    uf = W.util_funcs
+    z = G.load("util_norm")
+    n, d = int(z["in_n"]), int(z["in_feat_dim"])
+    a = sp.coo_matrix((z["in_val"], (z["in_row"], z["in_col"])), shape=(n, n)).tocsr()
+    f = sp.coo_matrix((z["in_feat_val"], (z["in_feat_row"], z["in_feat_col"])), shape=(n, d)).tocsr()
+    for got, tag, shape in ((uf.normalize(a), "normalize", (n, n)), (uf.preprocess_features(f), "preprocess", (n, d))):
+        m = got.to_scipy()
+        assert m.shape == shape
+        assert np.array_equal(m.indptr, z[f"out_{tag}_indptr"]) and np.array_equal(m.indices, z[f"out_{tag}_indices"])
+        close(m.data, z[f"out_{tag}_data"], rtol=1e-6, atol=0)      # float64 products, stored float32
+        close(np.asarray(got.todense()), sp.csr_matrix((z[f"out_{tag}_data"], z[f"out_{tag}_indices"],
+                                                        z[f"out_{tag}_indptr"]), shape=shape).toarray(), rtol=1e-6)
+    dense = torch.from_numpy(a.toarray()).float()
+    close(torch.tensor(uf.normalize(dense + torch.eye(n))), z["out_normalize_dense"], rtol=1e-6, atol=0)
+    close(uf.preprocess_features(torch.from_numpy(f.toarray()).float()), z["out_preprocess_dense"], rtol=1e-6, atol=0)
+    na = uf.normalize_adj(a).to_scipy()
+    assert np.array_equal(na.indptr, z["out_normalize_adj_indptr"])
+    assert np.array_equal(na.indices, z["out_normalize_adj_indices"])
+    close(na.data, z["out_normalize_adj_data"], rtol=1e-6, atol=0)
+    labels = torch.from_numpy(z["in_labels"])
+    nodes, bal = uf.dataset_edge_balance(a, labels)                      # weighted: aggregation-kernel path
+    close(nodes, z["out_balance_nodes"], rtol=0, atol=0)
+    close(bal, z["out_balance"], rtol=1e-5, atol=0)
+    nodes_b, bal_b = uf.dataset_edge_balance((a != 0).astype(np.float64), labels)   # binary: integer counters, exact
+    close(nodes_b, z["out_balance_nodes"], rtol=0, atol=0)
+    close(bal_b, z["out_balance_binary"], rtol=0, atol=0)
+    close(uf.dataset_edge_balance(torch.from_numpy(a.toarray()).float(), labels)[1], z["out_balance"], rtol=1e-5, atol=0)
+    with pytest.raises(ValueError):
+        W.CSRGraph.from_scipy(f)                                         # rectangular needs rectangular=True

@@ -216,3 +216,40 @@ def test_empty_graph():
     assert np.isnan(O.edge_homophily(e, e, np.array([0, 1, 0])))
     y = O.spmm(e, e, np.zeros(0, np.float32), 3, np.ones((3, 4), np.float32))
     assert y.shape == (3, 4) and not y.any()
+
+
+# ---------------------------------------------------------------------------
+# util_funcs.py normalisers next to the path: normalize :29, preprocess_features :39, normalize_adj :429,
+# dataset_edge_balance :439 (fixture tests/golden/util_norm.npz, make_golden.case_util_norm)
+# ---------------------------------------------------------------------------
+def _util_norm_inputs(z):
+    import scipy.sparse as sp
+    n, d = int(z["in_n"]), int(z["in_feat_dim"])
+    a = sp.coo_matrix((z["in_val"], (z["in_row"], z["in_col"])), shape=(n, n)).tocsr()
+    f = sp.coo_matrix((z["in_feat_val"], (z["in_feat_row"], z["in_feat_col"])), shape=(n, d)).tocsr()
+    return n, a, f
+
+
+def test_util_normalisers():
+    import scipy.sparse as sp
+    z = G.load("util_norm")
+    n, a, f = _util_norm_inputs(z)
+    for got, tag in ((O.normalize(a), "normalize"), (O.preprocess_features(f), "preprocess")):
+        m = sp.csr_matrix(got)
+        m.sort_indices()
+        assert np.array_equal(m.indptr, z[f"out_{tag}_indptr"]) and np.array_equal(m.indices, z[f"out_{tag}_indices"])
+        close(m.data, z[f"out_{tag}_data"], rtol=1e-12, atol=0)
+    dense = torch.from_numpy(a.toarray()).float()
+    close(O.normalize(dense + torch.eye(n)), z["out_normalize_dense"], rtol=1e-7, atol=0)
+    close(O.preprocess_features(torch.from_numpy(f.toarray()).float()), z["out_preprocess_dense"], rtol=1e-7, atol=0)
+    coo = a.tocoo()
+    r, c, v = O.normalize_adj(coo.row, coo.col, coo.data, n)
+    ref = sp.csr_matrix((z["out_normalize_adj_data"], z["out_normalize_adj_indices"], z["out_normalize_adj_indptr"]),
+                        shape=(n, n)).tocoo()
+    assert np.array_equal(r, ref.row) and np.array_equal(c, ref.col)
+    close(v, ref.data, rtol=1e-12, atol=0)
+    nodes, bal = O.dataset_edge_balance(coo.row, coo.col, coo.data, z["in_labels"], n)
+    close(nodes, z["out_balance_nodes"], rtol=0, atol=0)
+    close(bal, z["out_balance"], rtol=1e-12, atol=0)
+    _, bal_b = O.dataset_edge_balance(coo.row, coo.col, np.ones_like(coo.data), z["in_labels"], n)
+    close(bal_b, z["out_balance_binary"], rtol=0, atol=0)

@@ -17,8 +17,10 @@ __global__ void degree_scale_kernel(const int64_t *__restrict__ rowptr, const fl
       if (norm == WDGH_NORM_SYM) {
         if (rs == 0.0) rs = 1.0;  // util_funcs.py:422
         r = 1.0 / sqrt(rs);
+      } else if (norm == WDGH_NORM_SYM_RAW) {
+        r = (rs == 0.0) ? 0.0 : 1.0 / sqrt(rs);  // util_funcs.py:433-434: power(0, -0.5) = inf -> 0
       } else {
-        r = (rs == 0.0) ? 0.0 : 1.0 / rs;  // sk_normalize leaves all-zero rows untouched
+        r = (rs == 0.0) ? 0.0 : 1.0 / rs;  // sk_normalize leaves all-zero rows untouched; :31-32 inf -> 0
       }
       if (dinv) dinv[i] = (float)r;
       if (dinv64) dinv64[i] = r;
@@ -49,6 +51,14 @@ __global__ void degree_scale_kernel(const int64_t *__restrict__ rowptr, const fl
         if (rs == 0.0) rs = 1.0;
         r = pow(rs, -0.5);
         if (isinf(r)) r = 0.0;  // util_funcs.py:424
+      } else if (norm == WDGH_NORM_SYM_RAW) {
+        rs += self_loop ? 1.0 : 0.0;
+        r = pow(rs, -0.5);  // util_funcs.py:433 (NaN for a negative row sum, like numpy)
+        if (isinf(r)) r = 0.0;  // :434
+      } else if (norm == WDGH_NORM_RW_SUM) {
+        rs += self_loop ? 1.0 : 0.0;
+        r = 1.0 / rs;  // util_funcs.py:31 / :41, signed row sum
+        if (isinf(r)) r = 0.0;  // :32 / :42
       } else {
         ra += self_loop ? 1.0 : 0.0;  // l1 norm (sklearn normalize, util_funcs.py:386)
         r = (ra == 0.0) ? 0.0 : 1.0 / ra;
@@ -72,7 +82,7 @@ __global__ void scale_values_kernel(const int64_t *__restrict__ rowptr, const in
     for (int64_t q = s + lane; q < e; q += 32) {
       const double a = val ? (double)val[q] : 1.0;
       double v = di * a;
-      if (norm == WDGH_NORM_SYM) v = v * dinv64[col[q]];
+      if (norm == WDGH_NORM_SYM || norm == WDGH_NORM_SYM_RAW) v = v * dinv64[col[q]];
       out[q] = (float)v;
     }
   }
@@ -114,7 +124,7 @@ using namespace wdgh;
 extern "C" int wdgh_degree_scale(const int64_t *rowptr, const float *val, int64_t n, int norm, int add_self_loop,
                                  float *dinv, double *dinv64, uint8_t *deg_code, void *stream) {
   WDGH_REQUIRE(rowptr && (dinv || dinv64) && n >= 0, "wdgh_degree_scale: bad arguments");
-  WDGH_REQUIRE(norm == WDGH_NORM_RW || norm == WDGH_NORM_SYM, "wdgh_degree_scale: norm must be RW or SYM");
+  WDGH_REQUIRE(norm >= WDGH_NORM_RW && norm <= WDGH_NORM_SYM_RAW, "wdgh_degree_scale: norm must be RW, SYM, RW_SUM or SYM_RAW");
   WDGH_REQUIRE(deg_code == nullptr || val == nullptr, "wdgh_degree_scale: degree codes need a binary adjacency");
   if (n == 0) return 0;
   const int64_t ctas = val ? ceil_div(n, 8) : ceil_div(n, 256);
@@ -128,7 +138,7 @@ extern "C" int wdgh_degree_scale(const int64_t *rowptr, const float *val, int64_
 extern "C" int wdgh_scale_values(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n, int norm,
                                  const double *dinv64, float *out, void *stream) {
   WDGH_REQUIRE(rowptr && col && out && dinv64 && n >= 0, "wdgh_scale_values: bad arguments");
-  WDGH_REQUIRE(norm == WDGH_NORM_RW || norm == WDGH_NORM_SYM, "wdgh_scale_values: norm must be RW or SYM");
+  WDGH_REQUIRE(norm >= WDGH_NORM_RW && norm <= WDGH_NORM_SYM_RAW, "wdgh_scale_values: norm must be RW, SYM, RW_SUM or SYM_RAW");
   if (n == 0) return 0;
   scale_values_kernel<<<persistent_grid(ceil_div(n, 8), 8), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, norm,
                                                                                        dinv64, out);

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwdgh_b200.so")
 
 NORM_NONE, NORM_RW, NORM_SYM = 0, 1, 2
+NORM_RW_SUM, NORM_SYM_RAW = 3, 4   # scale modes of wdgh_degree_scale / wdgh_scale_values only (include/wdgh_b200.h)
 PLAN_HEADER = 8
 UNIT = 1024
 SC_MATCH_ALL, SC_MATCH_LAB, SC_N_LAB, SC_N_SELF, SC_N_EMPTY, SC_NBINS, SC_N_NODES_NSL, SC_N_MULTI_NEG = range(8)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NORM_NONE, NORM_RW, NORM_SYM, check, lib, ptr, stream_ptr
+from ._lib import NORM_NONE, NORM_RW, NORM_RW_SUM, NORM_SYM, NORM_SYM_RAW, check, lib, ptr, stream_ptr
 
 HEAVY_THRESHOLD = 512  # entries; longer rows are split into chunks of this many (degree binning)
 
@@ -48,6 +48,7 @@ class CSRGraph:
         self.n_global = int(n_global) if n_global is not None else int(n)
         self.threshold = int(threshold)
         self.device = rowptr.device
+        self.n_cols = self.n_global       # a rectangular row-scaled matrix (preprocess_features) overrides this
         self._plan = None
         self._rows = None
         self._dinv = {}
@@ -81,15 +82,21 @@ class CSRGraph:
         return cls.from_coo_indices(a.indices(), vals, a.shape[0], threshold)
 
     @classmethod
-    def from_scipy(cls, m, threshold=HEAVY_THRESHOLD, binary=False):
+    def from_scipy(cls, m, threshold=HEAVY_THRESHOLD, binary=False, rectangular=False):
+        """scipy sparse matrix -> resident CSR.  `rectangular=True` admits an n x d matrix (a sparse feature matrix):
+        such a container only supports the row scalings (`normalized(NORM_RW / NORM_RW_SUM)`) and the exports."""
         m = m.tocsr()
+        if m.shape[0] != m.shape[1] and not rectangular:
+            raise ValueError(f"adjacency must be square, got {m.shape}")
         m.sum_duplicates()
         m.sort_indices()
         dev = _dev()
         rowptr = torch.from_numpy(m.indptr.astype(np.int64)).to(dev)
         col = torch.from_numpy(m.indices.astype(np.int32)).to(dev)
         val = None if binary else torch.from_numpy(m.data.astype(np.float32)).to(dev)
-        return cls(rowptr, col, val, m.shape[0], threshold)
+        g = cls(rowptr, col, val, m.shape[0], threshold)
+        g.n_cols = int(m.shape[1])
+        return g
 
     @classmethod
     def from_csr(cls, rowptr, col, val, n, threshold=HEAVY_THRESHOLD):
@@ -162,17 +169,30 @@ class CSRGraph:
 
     def normalized(self, norm):
         """Materialised D^-1/2 A D^-1/2 (SYM) or D^-1 A (RW) of THIS matrix (no self-loop added)."""
+        if norm in (NORM_SYM, NORM_SYM_RAW) and self.n_cols != self.n:
+            raise ValueError("a symmetric scaling needs a square matrix")
         d64 = self.degree_scale(norm, False, want64=True)[1]
         out = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
         check(lib.wdgh_scale_values(ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n, norm, ptr(d64), ptr(out),
                                     stream_ptr()), "wdgh_scale_values")
         g = CSRGraph(self.rowptr, self.col, out, self.n, self.threshold)
-        g._plan, g._rows = self._plan, self._rows
+        g._plan, g._rows, g.n_cols = self._plan, self._rows, self.n_cols
         return g
 
     def to_torch_sparse(self):
         v = self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32, device=self.device)
-        return torch.sparse_coo_tensor(self.indices(), v, (self.n, self.n), is_coalesced=True)
+        return torch.sparse_coo_tensor(self.indices(), v, (self.n, self.n_cols), is_coalesced=True)
+
+    def to_scipy(self):
+        """Host copy as scipy CSR (float32 values) -- what the scipy-returning reference normalisers hand back."""
+        import scipy.sparse as sp
+        v = self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32, device=self.device)
+        return sp.csr_matrix((v.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.n, self.n_cols))
+
+    def todense(self):
+        """numpy matrix like scipy's `.todense()` (full_load_data densifies the row-normalised features this way)."""
+        return self.to_scipy().todense()
 
 
 # ---------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 """Drop-in mirror of the graph-statistics parts of the reference's `utils/util_funcs.py`.
 
-Normalisers run on the GPU through libwdgh_b200.so; the split / accuracy helpers are the
+Normalisers (normalize, preprocess_features, normalize_tensor, normalize_adj, sys_/row_normalized_adjacency)
+and dataset_edge_balance run on the GPU through libwdgh_b200.so; the split / accuracy helpers are the
 reference's host-side RNG logic (they must consume torch's global RNG identically so that
 seeded runs reproduce).  Dataset loaders (load_data, full_load_data*, utils/datasets.py) are
 out of scope of the hot path -- keep using the reference's.
@@ -26,6 +27,64 @@ def _to_graph(adj, binary=False) -> CSRGraph:
 def normalize_tensor(mx, symmetric=0):
     """Row-normalise (symmetric=0) or D^-1/2 M D^-1/2 (symmetric=1) a dense matrix.  util_funcs.py:365-380."""
     return G.normalize_dense(mx, 1 if symmetric else 0)
+
+
+def normalize(mx):
+    """Row-normalise: diag(1 / rowsum) @ mx, zero-sum rows stay zero.  util_funcs.py:29-36.
+
+    Dense input (torch / numpy; synthetic_plot.py:92 hands it `adj + eye`) -> dense float32 CUDA tensor, which the
+    caller's `torch.tensor(...)` wrapper accepts.  scipy sparse input (full_load_data, util_funcs.py:189-190) ->
+    resident CSRGraph holding f32(rowsum^-1 * a_ij), products formed in float64 like scipy's."""
+    if sp.issparse(mx):
+        return _to_graph(mx).normalized(G.NORM_RW_SUM)
+    return G.normalize_dense(mx, 0)
+
+
+def preprocess_features(features):
+    """Row-normalise the feature matrix.  util_funcs.py:39-46 (same arithmetic as `normalize`)."""
+    if sp.issparse(features):
+        return G.CSRGraph.from_scipy(features, rectangular=True).normalized(G.NORM_RW_SUM)
+    return G.normalize_dense(features, 0)
+
+
+def normalize_adj(adj):
+    """(A D^-1/2)^T D^-1/2 = D^-1/2 A^T D^-1/2, D = diag(row sums of A), as a resident CSRGraph.  util_funcs.py:429-436.
+    Zero row sums give a zero scale (`inf -> 0`), negative ones NaN, exactly like numpy's power(., -0.5)."""
+    g = _to_graph(adj)
+    scaled = g.normalized(G.NORM_SYM_RAW)            # D^-1/2 A D^-1/2 on A's pattern ...
+    t = scaled.to_torch_sparse().t().coalesce()      # ... and its transpose (index plumbing only)
+    return CSRGraph.from_coo_indices(t.indices(), t.values(), g.n)
+
+
+def dataset_edge_balance(adj, labels):
+    """Per class: (node count, adjacency mass inside the class, adjacency mass leaving it).  util_funcs.py:439-451.
+
+    A binary adjacency goes through the integer label-statistics kernels (exact counts); a weighted one through the
+    aggregation kernel, Z = A [onehot | 1 - onehot], followed by class-wise sums."""
+    lab = torch.as_tensor(labels).reshape(-1)
+    c = int(lab.max().item()) + 1
+    g = _to_graph(adj)
+    lab32, _ = G.pack_labels(lab)
+    binary = g.val is None or bool((g.val == 1).all().item())
+    if binary:
+        s = G.structure_counts_coo(g.indices(), g.n, lab32, c, hist_includes_self_loops=True)
+        inside = np.diag(s.hist).astype(np.float64)
+        nodes = s.class_count.astype(np.float64)
+        return nodes, np.stack([inside, s.class_deg.astype(np.float64) - inside], axis=1)
+    known = lab32 >= 0
+    onehot = torch.zeros((g.n, c), dtype=torch.float32, device=g.device)
+    onehot[known, lab32[known].long()] = 1.0
+    z = G.spmm(g, torch.cat([onehot, 1.0 - onehot], dim=1))          # [n, 2c]: mass into class k / into the rest
+    # class-wise row sums are one more aggregation: P[i, u] = 1 iff label(u) = i (rows >= c empty), sums = (P Z)[:c]
+    order = torch.argsort(torch.where(known, lab32, c).long(), stable=True)
+    count = torch.bincount(lab32[known].long(), minlength=c)
+    rowptr = torch.zeros(g.n + 1, dtype=torch.int64, device=g.device)
+    rowptr[1:c + 1] = torch.cumsum(count, 0)
+    rowptr[c + 1:] = rowptr[c]
+    pool = CSRGraph(rowptr, order[:int(rowptr[c].item())].to(torch.int32).contiguous(), None, g.n)
+    sums = G.spmm(pool, z)[:c].cpu().numpy().astype(np.float64)     # [c, 2c]
+    idx = np.arange(c)
+    return count.cpu().numpy().astype(np.float64), np.stack([sums[idx, idx], sums[idx, c + idx]], axis=1)
 
 
 def sys_normalized_adjacency(adj):
