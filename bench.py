@@ -108,7 +108,10 @@ def gen_rows(r0, r1, n, avg_deg, C, h, d, device, seed=1234, want_x=True):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 50` in the background from process start; `stop(t0, t1)` keeps the samples whose own
+    timestamp lies inside the wall-clock window [t0, t1] = warm-up + timed steps (B200_PROFILING.md clocks line).
+    Started early because nvidia-smi needs up to a second for its first sample on an 8-GPU box."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
@@ -123,36 +126,42 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def parse(text, t0, t1):
+        """CSV lines -> summary of the samples taken in [t0, t1] (seconds since the epoch, local clock)."""
+        import datetime
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in text.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if not (t0 - 0.025 <= ts <= t1 + 0.025):
+                    continue
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+    def stop(self, t0, t1):
         if self.proc is None:
-            return out
+            return self.parse("", t0, t1)
         time.sleep(0.15)
         self.proc.terminate()
         try:
             text, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in text.strip().splitlines():
-            f = [v.strip() for v in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                busy = float(f[7]) > 0  # the sampler starts before the warm-up: keep the samples taken under load
-                if not busy:
-                    continue
-                sm.append(float(f[0])), mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        return out
+            return self.parse("", t0, t1)
+        return self.parse(text, t0, t1)
 
 
 # ---------------------------------------------------------------------------
@@ -232,6 +241,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     W._lib.require_device()
+    sampler = ClockSampler(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     n, C, d = args.nodes, args.classes, args.dim
@@ -297,7 +307,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(device)  # samples with utilisation > 0 = warm-up + timed steps (both under load)
+    trace_stages = os.environ.get("WDGH_STAGE_TIMES") == "1" and hasattr(pipe, "_trace")
+    if trace_stages:
+        pipe._trace = False           # the per-stage events synchronise every step: keep them out of the timed steps
+    barrier()
+    t_load0 = time.time()             # clock samples are kept from here (warm-up + timed steps, all under load)
     for _ in range(max(args.warmup, 3)):
         counters, node_sum = step()
     barrier()
@@ -308,14 +322,27 @@ def main():
         counters, node_sum = step()
     ev1.record()
     barrier()
+    t_load1 = time.time()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = W.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load0, t_load1)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
     value = nnz / (ms * 1e-3) / 1e9
+
+    # ---- checksum of Y = A_hat X of the last step: sum and sum |.| over all ranks in float64.  The graph does not
+    # depend on the partition, so N = 1, rows/N and the 2-D partition must print the same two numbers (~1e-7).
+    y_last = y if world == 1 else pipe._y
+    y_chk = torch.zeros(2, dtype=torch.float64, device=device)
+    for a0 in range(0, r1 - r0, 1 << 20):
+        blk = y_last[a0:min(a0 + (1 << 20), r1 - r0)]
+        y_chk[0] += blk.sum(dtype=torch.float64)
+        y_chk[1] += blk.abs().sum(dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(y_chk)
+    y_chk = [float(v) for v in y_chk.tolist()]
 
     # ---- roofline of the dominant kernel (spmm_rowgroup_kernel), timed alone on this rank's shard ----
     if world == 1:
@@ -345,6 +372,10 @@ def main():
         def spmm_once():
             G.spmm(g, xs, W.NORM_SYM, True, out=ys, dinv=dinv, deg_code=code)
         rows_local = r1 - r0
+    if trace_stages:                  # one extra, untimed step with per-stage CUDA events
+        pipe._trace = True
+        step()
+        pipe._trace = False
     if getattr(pipe, "stage_ms", None) and os.environ.get("WDGH_STAGE_TIMES") == "1":
         print(f"[rank {rank}] stages: " + ", ".join(f"{k} {v:.2f}" for k, v in pipe.stage_ms), file=sys.stderr, flush=True)
     for _ in range(2):
@@ -386,7 +417,8 @@ def main():
     h = counters.cpu().numpy()
     metrics = {"edge_homophily_with_self_loops": float((h[0] + n) / (nnz + n)),
                "node_homophily": float(node_sum[0].item() / max(int(h[G._lib.SC_N_NODES_NSL]), 1)),
-               "class_pair_hist_total": int(h[G._lib.SC_HEADER + 2 * C:G._lib.SC_HEADER + 2 * C + C * C].sum())}
+               "class_pair_hist_total": int(h[G._lib.SC_HEADER + 2 * C:G._lib.SC_HEADER + 2 * C + C * C].sum()),
+               "y_sum": y_chk[0], "y_abs_sum": y_chk[1]}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
     e2e = None

@@ -660,6 +660,23 @@ def test_2d_partition_blocks_reduce_to_one_pass(W, d, world, n):
             W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_pad, part, W.NORM_SYM, True, dinv_pad, dcode, skip,
                                 False, False, True)
             parts.append(part)
+            if owner in (1, world - 2):
+                # WDGH_2D_SPLIT_FIRST: the same slice in phases -- the producer's own-shard columns first, then the
+                # partner shards' columns below / above them with `y +=`, split rows with the last phase
+                prod = i * pc + j
+                seg = W.graph.column_segments(sg, [prod * blk, (prod + 1) * blk])
+                split = torch.full((blk, d), float("nan"), device="cuda")
+                W.graph.spmm_ranged(sg, seg[0], seg[1], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode, skip,
+                                    False, False, False)
+                below, above = i > 0, i < grid.pr - 1
+                if below:
+                    W.graph.spmm_ranged(sg, sg.rowptr[:-1], seg[0], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode,
+                                        skip, True, False, not above)
+                if above:
+                    W.graph.spmm_ranged(sg, seg[1], sg.rowptr[1:], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode,
+                                        skip, True, False, True)
+                rows_s = r1 - r0
+                assert (split[:rows_s] - part[:rows_s]).abs().max().item() <= 1e-5 * part[:rows_s].abs().max().item()
         y = torch.empty((r1 - r0, d), device="cuda")
         W.graph.reduce_finalize(parts, x_pad, y, W.NORM_SYM, True, dinv_pad, r0)
         err = (y - y_ref[r0:r1]).abs().max().item()

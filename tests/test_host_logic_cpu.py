@@ -1,5 +1,6 @@
 """Host-side logic of the mirror that needs no GPU: RNG-compatible splits, accuracy, masks."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import ref_port as O
@@ -69,3 +70,39 @@ def test_grid2d_blocks_tile_the_matrix():
     # ranks of a row group cover the rows of that group once each
     rows = sorted(r for s in g.row_group_ranks(0) for r in range(*g.part.bounds(s)))
     assert rows == list(range(0, 4 * g.part.block))
+
+
+@pytest.mark.parametrize("world,pr", [(4, 2), (8, 2), (8, 4), (6, 2)])
+def test_grid2d_schedule_and_receive_slots_agree(world, pr):
+    """What rank r pushes in step k lands in slot k of the owner, and the owner expects exactly r there; every
+    foreign slice of a row group is produced once per column group, the own slice comes last."""
+    from wdgh_b200.sharded import Grid2D
+    g = Grid2D(997, world, pr)
+    for r in range(world):
+        i, j = g.coords(r)
+        sched = g.schedule(r)
+        assert [k for k, _, _ in sched] == list(range(1, g.pc + 1))
+        assert sorted(s for _, s, _ in sched) == list(range(g.pc))           # every slice of the row group once
+        assert sched[-1][1:] == (j, r)                                         # own slice last, nothing to send
+        for k, s, owner in sched[:-1]:
+            assert g.coords(owner) == (i, s) and owner != r
+            assert g.slot_source(owner, k) == r
+        # the pc - 1 receive slots of r are fed by pc - 1 distinct ranks of its row group
+        sources = [g.slot_source(r, k) for k in range(1, g.pc)]
+        assert sorted(sources + [r]) == g.row_group_ranks(i)
+
+
+def test_bench_clock_sampler_keeps_only_samples_inside_the_window():
+    import datetime
+    import bench
+
+    def line(t, sm, cap):
+        ts = datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return f"{ts}, {sm}, 1965, 512.3, Not Active, Not Active, Not Active, {cap}, 97"
+
+    t = 1_792_000_000.0
+    text = "\n".join([line(t - 5.0, 210, "Not Active"), line(t + 0.1, 1600, "Active"), line(t + 0.2, 1700, "Not Active"),
+                      line(t + 0.3, 1650, "Not Active"), line(t + 9.0, 300, "Not Active"), "garbage"])
+    out = bench.ClockSampler.parse(text, t, t + 0.35)
+    assert out == {"sm_mhz": 1650.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    assert bench.ClockSampler.parse("", t, t + 1)["samples"] == 0

@@ -383,6 +383,15 @@ class Cuda2DShardedStats:
         # WDGH_2D_DIRECT=1: the aggregation kernel stores foreign row slices straight into the owner's receive
         # buffer over NVLink (no local partial buffer, no copy-engine push)
         self._direct = os.environ.get("WDGH_2D_DIRECT", "0") == "1"
+        # WDGH_2D_SPLIT_FIRST=1: the first row slice is aggregated in two phases -- the entries whose source node lies
+        # in this rank's own shard while the partner shards are still being pulled, the rest after they arrived
+        # (`y +=`, like the 1-D phased step) -- and the pulls start right after the first small all-gather.
+        self._split_first = os.environ.get("WDGH_2D_SPLIT_FIRST", "0") == "1" and grid.pr > 1
+        self._seg_first = None
+        if self._split_first:
+            _, s1, _ = grid.schedule(rank)[0]
+            self._seg_first = G.column_segments(self.slices[s1], [rank * blk, (rank + 1) * blk])
+        self._ev_ready = torch.cuda.Event()
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -400,6 +409,10 @@ class Cuda2DShardedStats:
         marks = [] if self._trace else None
         self._mark(marks, "start")
         labels_full = _all_gather_rows(self.labels_local, self.group)
+        if self._split_first:
+            # every peer has passed its first collective of this step, i.e. finished the previous step's reads and
+            # the writes of its shard: the pulls may start now, next to the remaining small all-gathers
+            self._ev_ready.record(cur)
         dinv_full = code_full = None
         if norm != _lib.NORM_NONE:
             self.g1d._dinv.clear()
@@ -408,7 +421,10 @@ class Cuda2DShardedStats:
             code_full = _all_gather_rows(_pad_rows(code, blk), self.group) if code is not None else None
         self._mark(marks, "small all-gathers")
         # 1. feature shards of my column group: partner shards are pulled, my own is already in place
-        self._copy.wait_stream(cur)
+        if self._split_first:
+            self._copy.wait_event(self._ev_ready)
+        else:
+            self._copy.wait_stream(cur)
         with torch.cuda.stream(self._copy):
             for src, buf in self._peer_x.items():
                 self.x_full[src * blk:(src + 1) * blk].copy_(buf, non_blocking=True)
@@ -416,15 +432,34 @@ class Cuda2DShardedStats:
         # 2. label pass on the 1-D shard, under the pulls
         self._scratch = G.structure_counts_raw(self.g1d, labels_full, self.c, self._scratch)
         self._mark(marks, "label pass")
-        cur.wait_event(self._ev_x)
-        self._mark(marks, "wait pulls")
+        if not self._split_first:
+            cur.wait_event(self._ev_x)
+            self._mark(marks, "wait pulls")
         # 3. row slices of my block: foreign slices first, each pushed to its owner while the next one is aggregated
         for k, s, owner in grid.schedule(r):
             g = self.slices[s]
             direct = self._direct and s != j
             out = self._peer_recv[owner][k] if direct else self.partial[s]
-            G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, out, norm, add_self_loop,
-                          dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True)
+            if k == 1 and self._split_first:
+                lo, hi = self._seg_first[0], self._seg_first[1]
+                # own-shard columns first (no dependence on the pulls) ...
+                G.spmm_ranged(g, lo, hi, self.x_full, out, norm, add_self_loop, dinv_full, code_full, self._skip[s],
+                              accumulate=False, finalize=False, run_split_rows=False)
+                self._mark(marks, f"slice {s} local columns")
+                cur.wait_event(self._ev_x)
+                self._mark(marks, "wait pulls")
+                # ... then the columns of the partner shards below / above it; split rows with the last phase
+                below, above = i > 0, i < grid.pr - 1
+                if below:
+                    G.spmm_ranged(g, g.rowptr[:-1], lo, self.x_full, out, norm, add_self_loop, dinv_full, code_full,
+                                  self._skip[s], accumulate=True, finalize=False, run_split_rows=not above)
+                if above:
+                    G.spmm_ranged(g, hi, g.rowptr[1:], self.x_full, out, norm, add_self_loop, dinv_full, code_full,
+                                  self._skip[s], accumulate=True, finalize=False, run_split_rows=True)
+            else:
+                G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, out, norm, add_self_loop,
+                              dinv_full, code_full, self._skip[s], accumulate=False, finalize=False,
+                              run_split_rows=True)
             self._mark(marks, f"slice {s}")
             if s != j and not direct:
                 self._ev_slice[s].record(cur)

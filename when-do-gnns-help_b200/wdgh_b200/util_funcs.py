@@ -67,10 +67,10 @@ def dataset_edge_balance(adj, labels):
     lab32, _ = G.pack_labels(lab)
     binary = g.val is None or bool((g.val == 1).all().item())
     if binary:
-        s = G.structure_counts_coo(g.indices(), g.n, lab32, c, hist_includes_self_loops=True)
-        inside = np.diag(s.hist).astype(np.float64)
-        nodes = s.class_count.astype(np.float64)
-        return nodes, np.stack([inside, s.class_deg.astype(np.float64) - inside], axis=1)
+        pairs = G.structure_counts_coo(g.indices(), g.n, lab32, c, hist_includes_self_loops=True)   # diagonal kept
+        rows = G.structure_counts(g, lab32, c)                    # class sizes + stored entries per class of the row
+        inside = np.diag(pairs.hist).astype(np.float64)
+        return rows.class_count.astype(np.float64), np.stack([inside, rows.class_deg.astype(np.float64) - inside], axis=1)
     known = lab32 >= 0
     onehot = torch.zeros((g.n, c), dtype=torch.float32, device=g.device)
     onehot[known, lab32[known].long()] = 1.0
