@@ -106,3 +106,24 @@ def test_bench_clock_sampler_keeps_only_samples_inside_the_window():
     out = bench.ClockSampler.parse(text, t, t + 0.35)
     assert out == {"sm_mhz": 1650.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
     assert bench.ClockSampler.parse("", t, t + 1)["samples"] == 0
+
+
+def test_bench_generator_is_partition_and_flag_independent(monkeypatch):
+    """The synthetic graph must be the same whoever generates a row range: any sharding, with or without features
+    (the 2-D partition regenerates its peers' rows with want_x=False)."""
+    import bench
+    monkeypatch.setattr(bench, "TILE_ROWS", 1000)
+    dev = torch.device("cpu")
+    n = 4700
+    rp, col, x, lab = bench.gen_rows(0, n, n, 6.0, 5, 0.3, 8, dev)
+    assert rp[0] == 0 and rp[-1] == col.shape[0] and x.shape == (n, 8) and lab.shape == (n,)
+    for r0, r1 in ((0, 1175), (1175, 2350), (2350, 4700), (3300, 3301)):
+        for want_x in (True, False):
+            rp_s, col_s, x_s, lab_s = bench.gen_rows(r0, r1, n, 6.0, 5, 0.3, 8, dev, want_x=want_x)
+            assert torch.equal(rp_s, rp[r0:r1 + 1] - rp[r0])
+            assert torch.equal(col_s, col[rp[r0]:rp[r1]])
+            assert torch.equal(lab_s, lab[r0:r1])
+            if want_x:
+                assert torch.equal(x_s, x[r0:r1])
+            else:
+                assert x_s is None

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Multi-GPU cross-check of the partitioned pipelines ON THE SAME GRAPH, in one launch:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 \
+        tools/check_partitions.py [--nodes 4000000 1000003]
+
+Every rank builds its row shard of the bench generator's graph and runs
+
+    1d-plain   NCCL all-gather of the features, then ONE aggregation launch (the N = 1 kernel on a row shard)
+    1d-phased  peer-mapped shards pulled by the copy engines, one `y +=` phase per arriving shard
+    2d         row group x column group blocks, partial slices pushed to the owners, reduce + finalize
+    2d-split   WDGH_2D_SPLIT_FIRST=1 (first slice in two phases under the pulls)
+    2d-direct  WDGH_2D_DIRECT=1 (foreign slices stored straight into the owner's memory over NVLink)
+
+and compares each result (Y rows of the rank, all-reduced counters, node sum) with 1d-plain.  Rank 0 prints one JSON
+line and exits non-zero on a mismatch.  Y tolerance 2e-6 of max |Y| (float32 sums in a different association);
+counters must be identical.  (tests/test_gpu_multi.py runs this under pytest when >= 4 GPUs are visible.)
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "when-do-gnns-help_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def check(args, n, world, rank, device, bench, W, G, CudaShardedStats, Cuda2DShardedStats, Grid2D, RowPartition):
+    C, d = args.classes, args.dim
+    args.nodes = n                     # bench.make_slice_graphs reads the node count from args
+    part = RowPartition(n, world)
+    r0, r1 = part.bounds(rank)
+    rowptr, col, x_local, labels_local = bench.gen_rows(r0, r1, n, args.avg_degree, C, args.homophily, d, device)
+    g = G.CSRGraph(rowptr, col, None, r1 - r0, row_offset=r0, n_global=n)
+
+    def run(pipe):
+        for _ in range(2):                      # the second step also exercises buffer reuse across steps
+            y, counters, node_sum = pipe.step(W.NORM_SYM, True)
+        torch.cuda.synchronize()
+        return y.clone(), counters.clone(), node_sum.clone()
+
+    results = {}
+    results["1d-plain"] = run(CudaShardedStats(g, part, rank, x_local, labels_local, C, phased=False))
+    results["1d-phased"] = run(CudaShardedStats(g, part, rank, x_local, labels_local, C, phased=True))
+    if world >= 4 and world % 2 == 0:
+        grid2 = Grid2D(n, world, 2)
+        slices = bench.make_slice_graphs(G, grid2, rank, rowptr, col, args, device)
+        for name, env in (("2d", {}), ("2d-split", {"WDGH_2D_SPLIT_FIRST": "1"}), ("2d-direct", {"WDGH_2D_DIRECT": "1"})):
+            for k in ("WDGH_2D_SPLIT_FIRST", "WDGH_2D_DIRECT"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            results[name] = run(Cuda2DShardedStats(grid2, rank, slices, g, x_local, labels_local, C))
+
+    y_ref, cnt_ref, ns_ref = results["1d-plain"]
+    scale = torch.tensor([float(y_ref.abs().max())], dtype=torch.float64, device=device)
+    dist.all_reduce(scale, op=dist.ReduceOp.MAX)
+    report, ok = {}, True
+    for name, (y, cnt, ns) in results.items():
+        err = torch.tensor([float((y - y_ref).abs().max())], dtype=torch.float64, device=device)
+        bad = torch.tensor([int(not torch.equal(cnt, cnt_ref))], dtype=torch.int64, device=device)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bad)
+        rel = float(err.item() / scale.item())
+        ns_rel = abs(float(ns[0]) - float(ns_ref[0])) / max(abs(float(ns_ref[0])), 1e-30)
+        report[name] = {"y_max_err_rel": rel, "counters_equal": int(bad.item()) == 0, "node_sum_rel": ns_rel}
+        ok &= rel <= 2e-6 and int(bad.item()) == 0 and ns_rel <= 1e-12
+    return {"nodes": n, "results": report}, ok
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, nargs="+", default=[4_000_000, 1_000_003],
+                    help="graph sizes to check, one after the other (a size that is not a multiple of the world size "
+                         "exercises the padded last shard)")
+    ap.add_argument("--avg-degree", type=float, default=20.0)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--homophily", type=float, default=0.3)
+    args = ap.parse_args()
+
+    import bench
+    import wdgh_b200 as W
+    from wdgh_b200 import graph as G
+    from wdgh_b200.sharded import Cuda2DShardedStats, CudaShardedStats, Grid2D, RowPartition
+
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    W._lib.require_device()
+    dist.init_process_group("nccl", device_id=device)
+    reports, all_ok = [], True
+    for n in list(args.nodes):
+        rep, ok = check(args, n, world, rank, device, bench, W, G, CudaShardedStats, Cuda2DShardedStats, Grid2D,
+                        RowPartition)
+        reports.append(rep)
+        all_ok &= ok
+        torch.cuda.empty_cache()
+    ok = all_ok
+    if rank == 0:
+        print(json.dumps({"check": "partitions", "n_gpus": world, "dim": args.dim, "ok": bool(ok), "graphs": reports}),
+              flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
