@@ -44,6 +44,9 @@ inline int fail_cuda(cudaError_t e, const char *where) {
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached multiProcessorCount of the current device
+// Zeroed 64-bit ticket counter for one launch of a row-group kernel (memset ordered on `st`).  One ring of 64 slots per
+// device, handed out round-robin: up to 64 launches may be in flight per device.  nullptr on allocation failure.
+unsigned long long *ticket_slot(cudaStream_t st);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

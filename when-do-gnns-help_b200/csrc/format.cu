@@ -6,6 +6,9 @@
 // merges or inserts the diagonal.
 #include <limits.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace wdgh {
@@ -23,6 +26,21 @@ int sm_count() {
     cached[dev] = v;
   }
   return cached[dev];
+}
+
+unsigned long long *ticket_slot(cudaStream_t st) {
+  static unsigned long long *ring[64] = {nullptr};
+  static std::atomic<unsigned> next{0};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring[dev] && cudaMalloc(&ring[dev], 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  }
+  unsigned long long *slot = ring[dev] + (next.fetch_add(1) & 63u);
+  if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
+  return slot;
 }
 
 // ---------------------------------------------------------------------------

@@ -1052,16 +1052,6 @@ static int rowgroup_enabled() {
   }
   return cached;
 }
-// ticket counters of the row-group kernel: one slot per launch, 64 launches may be in flight
-static unsigned long long *ticket_slot(cudaStream_t st) {
-  static unsigned long long *ring = nullptr;
-  static unsigned next = 0;
-  if (!ring && cudaMalloc(&ring, 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-  unsigned long long *slot = ring + (next++ & 63u);
-  if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
-  return slot;
-}
-
 template <int VEC, int NCH, bool HAS_VAL>
 static int launch_rowgroup(const SpmmArgs &a) {
   constexpr int TILE = 32 * VEC * NCH;

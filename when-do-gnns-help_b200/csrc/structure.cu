@@ -526,22 +526,13 @@ static int label_rowgroup_enabled() {
   }
   return cached;
 }
-static unsigned long long *label_ticket_slot(cudaStream_t st) {
-  static unsigned long long *ring = nullptr;
-  static unsigned next = 0;
-  if (!ring && cudaMalloc(&ring, 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-  unsigned long long *slot = ring + (next++ & 63u);
-  if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
-  return slot;
-}
-
 // per-row edge pass for one label representation
 template <typename L>
 static int launch_edge_rows(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz, const L *labels, int C,
                             int64_t threshold, unsigned long long *cnt, int32_t *deg_nsl, int32_t *match_nsl,
                             size_t hist_smem, cudaStream_t st, int64_t row_offset) {
   if (label_rowgroup_enabled()) {
-    unsigned long long *tickets = label_ticket_slot(st);
+    unsigned long long *tickets = ticket_slot(st);
     if (tickets == nullptr) return fail_cuda(cudaErrorMemoryAllocation, "structure: ticket counter");
     const int64_t n_groups = ceil_div(n, 32);
     structure_rowgroup_kernel<L><<<persistent_grid(ceil_div(n_groups, 8), 4), 256, hist_smem, st>>>(
