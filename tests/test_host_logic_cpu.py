@@ -127,3 +127,27 @@ def test_bench_generator_is_partition_and_flag_independent(monkeypatch):
                 assert torch.equal(x_s, x[r0:r1])
             else:
                 assert x_s is None
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's
+    keys; under torchrun only rank 0 works and prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--nodes", "20000",
+           "--cpu-sample-nodes", "20000", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=root, env={**os.environ, "RANK": "0"})
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert out.returncode == 0 and len(lines) == 1, out.stderr[-1500:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "GEdges/s" and line["higher_is_better"] is True
+    assert line["metric"] == "aggregation_plus_homophily_throughput" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("csbm-h power-law graph")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=root, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
