@@ -181,12 +181,9 @@ def spmm_projection(adj, features, out, tag):
 # --------------------------------------------------------------------------
 # case 1: Cora through the homophily_tests.py small-dataset flow
 # --------------------------------------------------------------------------
-def case_cora():
-    adj_sp, feats, labels = uf.load_data("cora")  # util_funcs.py:49
-    labels = torch.LongTensor(np.argmax(labels, axis=-1))
-    feats_sp = sp.csr_matrix(feats)
-    features_raw = torch.FloatTensor(np.asarray(feats.todense()))
-    A = uf.sparse_mx_to_torch_sparse_tensor(adj_sp).coalesce()  # raw, binary, no self-loops
+def _small_dataset_flow(name, adj_sp, feats_sp, features_raw, labels, kr_sample_max, kr_epochs):
+    """homophily_tests.py small-dataset flow (:78-87 normalisation, :108-137 metric dispatch) on one loaded dataset."""
+    A = uf.sparse_mx_to_torch_sparse_tensor(adj_sp).coalesce()  # raw, binary, no normalisation
     n = labels.shape[0]
     out = {}
     out["in_n"] = np.int64(n)
@@ -210,7 +207,7 @@ def case_cora():
             out[f"{k}__sym{sym}"] = v
     # aggregation homophily + KR are computed on the RAW adjacency (homophily_tests.py:120,135)
     gram_metrics(A, features_raw, labels, out, sample_n=96)
-    kr_metric(A, features_raw, labels, out, sample_max=500, epochs=6)
+    kr_metric(A, features_raw, labels, out, sample_max=kr_sample_max, epochs=kr_epochs)
     # scipy-side normalisers of the LINKX flow (homophily_tests.py:99-104)
     a_sym = uf.sparse_mx_to_torch_sparse_tensor(uf.sys_normalized_adjacency(adj_sp)).coalesce()
     a_rw = uf.sparse_mx_to_torch_sparse_tensor(uf.row_normalized_adjacency(adj_sp)).coalesce()
@@ -219,7 +216,36 @@ def case_cora():
     out["out_sys_norm_index"] = t2n(a_sym.indices()).astype(np.int32)
     spmm_projection(a_sym, features, out, "sys")
     spmm_projection(a_rw, features, out, "rw")
-    save("cora", **out)
+    save(name, **out)
+
+
+def case_cora():
+    adj_sp, feats, labels = uf.load_data("cora")  # util_funcs.py:49
+    labels = torch.LongTensor(np.argmax(labels, axis=-1))
+    _small_dataset_flow("cora", adj_sp, sp.csr_matrix(feats), torch.FloatTensor(np.asarray(feats.todense())), labels,
+                        kr_sample_max=500, kr_epochs=6)
+
+
+# --------------------------------------------------------------------------
+# case 1b: the other datasets shipped with the reference, loaded by its own loaders: citeseer (Planetoid files,
+# util_funcs.py:49) and the heterophilous WebKB / actor graphs (new_data/*, full_load_data_large :291-338)
+# --------------------------------------------------------------------------
+def case_datasets():
+    import networkx as nx  # the reference's loader needs it (full_load_data_large)
+    assert nx is not None
+    for name, sample_max in (("citeseer", 500), ("texas", 60), ("cornell", 60), ("wisconsin", 80), ("film", 300)):
+        if name == "citeseer":
+            adj_sp, feats, onehot = uf.load_data("citeseer")
+            labels = torch.LongTensor(np.argmax(onehot, axis=-1))
+            features_raw = torch.FloatTensor(np.asarray(feats.todense()))
+        else:
+            adj_t, features_raw, labels = uf.full_load_data_large(name)
+            adj_t = adj_t.coalesce()
+            idx = t2n(adj_t.indices())
+            adj_sp = sp.coo_matrix((t2n(adj_t.values()).astype(np.float64), (idx[0], idx[1])), shape=tuple(adj_t.shape))
+            features_raw, labels = features_raw.float().cpu(), labels.long().cpu()
+        _small_dataset_flow(f"ds_{name}", adj_sp, sp.csr_matrix(features_raw.numpy()), features_raw, labels,
+                            kr_sample_max=sample_max, kr_epochs=4)
 
 
 # --------------------------------------------------------------------------
@@ -408,8 +434,8 @@ def case_util_norm():
 
 
 if __name__ == "__main__":
-    cases = {"plot": case_plot_variants, "cora": case_cora, "synthetic": case_synthetic, "edge": case_edge_cases,
-             "util_norm": case_util_norm}
+    cases = {"plot": case_plot_variants, "cora": case_cora, "datasets": case_datasets, "synthetic": case_synthetic,
+             "edge": case_edge_cases, "util_norm": case_util_norm}
     for name in (sys.argv[1:] or list(cases)):     # no argument = regenerate everything
         cases[name]()
     os.chdir(_cwd)

@@ -140,9 +140,12 @@ def check_kr(W, z, A, x, labels, tag=""):
 
 
 # ---------------------------------------------------------------------------
-def test_cora(W):
+@pytest.mark.parametrize("name", ["cora"] + G.names("ds_"))
+def test_reference_datasets(W, name):
+    """Cora + the other datasets the reference ships (citeseer, texas, cornell, wisconsin, film) through the
+    homophily_tests.py small-dataset flow, against the unmodified reference's outputs."""
     uf, hm = W.util_funcs, W.homophily_metrics
-    z = G.load("cora")
+    z = G.load(name)
     n = int(z["in_n"])
     labels = z["in_labels"]
     ei = z["in_edge_index"].astype(np.int64)

@@ -91,8 +91,11 @@ def check_kr(z, row, col, val, n, x, labels, tag=""):
 
 
 # ---------------------------------------------------------------------------
-def test_cora():
-    z = G.load("cora")
+@pytest.mark.parametrize("name", ["cora"] + G.names("ds_"))
+def test_reference_datasets(name):
+    """Cora + the other datasets the reference ships (citeseer, texas, cornell, wisconsin, film), loaded by the
+    reference's own loaders and pushed through the homophily_tests.py small-dataset flow."""
+    z = G.load(name)
     n = int(z["in_n"])
     labels = z["in_labels"]
     ei = z["in_edge_index"].astype(np.int64)
