@@ -13,7 +13,7 @@ Every rank builds its row shard of the bench generator's graph and runs
     2d-direct  WDGH_2D_DIRECT=1 (foreign slices stored straight into the owner's memory over NVLink)
 
 and compares each result (Y rows of the rank, all-reduced counters, node sum) with 1d-plain.  Rank 0 prints one JSON
-line and exits non-zero on a mismatch.  Y tolerance 2e-6 of max |Y| (float32 sums in a different association);
+line and exits non-zero on a mismatch.  Y tolerance 5e-6 of max |Y| (float32 sums in a different association);
 counters must be identical.  (tests/test_gpu_multi.py runs this under pytest when >= 4 GPUs are visible.)
 """
 import argparse
@@ -68,7 +68,7 @@ def check(args, n, world, rank, device, bench, W, G, CudaShardedStats, Cuda2DSha
         rel = float(err.item() / scale.item())
         ns_rel = abs(float(ns[0]) - float(ns_ref[0])) / max(abs(float(ns_ref[0])), 1e-30)
         report[name] = {"y_max_err_rel": rel, "counters_equal": int(bad.item()) == 0, "node_sum_rel": ns_rel}
-        ok &= rel <= 2e-6 and int(bad.item()) == 0 and ns_rel <= 1e-12
+        ok &= rel <= 5e-6 and int(bad.item()) == 0 and ns_rel <= 1e-12
     return {"nodes": n, "results": report}, ok
 
 
