@@ -1019,7 +1019,8 @@ static int launch_stream(const SpmmArgs &a) {
   return 0;
 }
 
-// 0 = plain row kernels, 1 = persistent pipelined rows (default), 2 = nnz-balanced cp.async stream
+// WDGH_SPMM_VARIANT: 0 = plain row kernels, 1 (default) = persistent kernels (row groups, or per-row pipelined with
+// WDGH_ROWGROUP=0), 2 = nnz-balanced cp.async stream
 static int wide_variant() {
   static int cached = -1;
   if (cached < 0) {

@@ -1,14 +1,21 @@
-"""1-D row-partitioned execution of the hot path over N GPUs (one process per GPU).
+"""Partitioned execution of the hot path over N GPUs (one process per GPU).
 
-Rank r owns a contiguous block of rows of the adjacency (CSR with GLOBAL column ids), the
-matching feature rows and labels.  One step =
-    all-gather(features, labels, degree scales)            -- NCCL over NVLink (gloo in CPU tests)
-    local  A_hat[rows_r, :] X  and local label statistics  -- the same CUDA kernels as on one GPU
-    all-reduce(class histograms + counters)                -- SUM (MAX for the bincount length)
-There is no other data-path collective: the aggregation output stays row-sharded.
+Nodes are owned 1-D: rank r holds a contiguous block of rows of the adjacency (CSR with GLOBAL column ids), the
+matching feature rows and labels.  Two pipelines share that ownership:
 
-Only `torch.distributed` plumbing and index arithmetic live here; the local compute is injected
-through two methods so that the world_size-2 gloo tests can drive the same plumbing on CPU.
+* `ShardedStats` / `CudaShardedStats` -- 1-D row partition.  One step =
+      all-gather(labels, degree scales)                      -- NCCL over NVLink (gloo in CPU tests)
+      features of the other ranks                            -- NCCL all-gather, or copy-engine pulls of peer-mapped
+                                                                shards with one aggregation phase per arriving shard
+      local  A_hat[rows_r, :] X  and local label statistics  -- the same CUDA kernels as on one GPU
+      all-reduce(class histograms + counters)                -- SUM (MAX for the bincount length)
+* `Grid2D` / `Cuda2DShardedStats` -- 2-D (row group x column group) partition for N >= 4: a rank aggregates the block
+  A[rows of its row group, columns of its column group], needs only its column group's feature shards and pushes
+  partial row slices to their owners (copy engines over NVLink), where `wdgh_reduce_finalize` completes them.
+
+The aggregation output stays row-sharded in both.  Only `torch.distributed` plumbing and index arithmetic live here;
+in `ShardedStats` the local compute is injected through two methods so that the gloo tests can drive the same
+plumbing on CPU.
 """
 from __future__ import annotations
 
