@@ -23,7 +23,6 @@ import random
 import time
 
 import numpy as np
-import scipy
 import torch
 from scipy.stats import ttest_ind
 

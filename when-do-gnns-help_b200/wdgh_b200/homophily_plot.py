@@ -16,7 +16,6 @@ kernels as `wdgh_b200.homophily_metrics`.  Differences of the plot variants that
 from __future__ import annotations
 
 import math
-import time
 
 import numpy as np
 import torch
