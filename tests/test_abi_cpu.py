@@ -64,3 +64,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as strict C99 and a C program must link against the library
+    (a cgo / JNI / ctypes-free consumer sees exactly this).  No compute call: there is no GPU here."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "wdgh_b200.h"\n'
+                   'int main(void) {\n'
+                   '  int sm = 0, major = 0, minor = 0;\n'
+                   '  (void)wdgh_device_info(&sm, &major, &minor);   /* fails without a device, must not crash */\n'
+                   '  return (wdgh_version() == WDGH_VERSION && wdgh_last_error() != 0) ? 0 : 1;\n'
+                   '}\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "when-do-gnns-help_b200", "wdgh_b200")
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe),
+                           f"-L{libdir}", "-lwdgh_b200", f"-Wl,-rpath,{libdir}"])
+    assert subprocess.run([str(exe)], timeout=60).returncode == 0
