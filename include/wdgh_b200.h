@@ -69,18 +69,18 @@ int wdgh_argmax_rows(const float *m, int64_t n, int64_t c, int64_t ld, int32_t *
  * many entries; everything else is handled one row per warp / sub-warp group.
  * The plan lives in caller-provided device memory and is reused by
  * wdgh_spmm_csr and wdgh_structure_counts for the same rowptr.
- * The plan also records, for every "stream unit" of WDGH_UNIT consecutive stored entries, the row
- * that contains the unit's first entry (the nnz-balanced SpMM walks units, not rows).
- *   plan_i64  : int64[WDGH_PLAN_WORDS(capacity, nnz)]  (device)
+ *   plan_i64  : int64[WDGH_PLAN_WORDS(capacity)]  (device).  Words 8..11 of the header are the ticket counters of
+ *               the persistent row-group kernels (zeroed here, re-armed by the last CTA of every launch): the plan
+ *               is therefore written by wdgh_spmm_csr* / wdgh_structure_counts, and one plan must not be used by two
+ *               launches that run concurrently on different streams (they would also share `partial`).
  *   capacity  : >= 2 * nnz / heavy_threshold + 2       (upper bound on the number of chunks)
  *   plan_host : int64[8] HOST array the later calls take alongside plan_i64
  * SYNCHRONOUS (reads the two counters back to size the later launches). */
-#define WDGH_PLAN_HEADER 8
-#define WDGH_UNIT 1024
-#define WDGH_PLAN_WORDS(capacity, nnz) (WDGH_PLAN_HEADER + 3 * (capacity) + ((nnz) + WDGH_UNIT - 1) / WDGH_UNIT)
+#define WDGH_PLAN_HEADER 16
+#define WDGH_PLAN_WORDS(capacity) (WDGH_PLAN_HEADER + 3 * (capacity))
 int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t nnz, int64_t heavy_threshold,
                     int64_t *plan_i64, int64_t capacity,
-                    int64_t *plan_host /* int64[8] out: n_heavy, n_chunks, threshold, capacity, unit, n_units, nnz, 0 */,
+                    int64_t *plan_host /* int64[8] out: n_heavy, n_chunks, threshold, capacity, 0, 0, nnz, 0 */,
                     void *stream);
 
 /* ---- normalisation (util_funcs.py:365-390, 418-426) ---------------------- */
@@ -115,8 +115,7 @@ int wdgh_normalize_dense(const float *x, int64_t n, int64_t d, int64_t ld,
  *   dinv     : float32[n] from wdgh_degree_scale (required iff norm != NONE)
  *   plan_i64 / plan_host : from wdgh_plan_build (required)
  *   partial  : float32[n_chunks * roundup(d,4)] scratch for the partial sums of split rows, n_chunks =
- *              plan_host[1] (may be NULL if 0).  The experimental nnz-balanced variant (environment
- *              WDGH_SPMM_VARIANT=2) needs max(n_chunks, 2 * plan_host[5]) rows instead.
+ *              plan_host[1] (may be NULL if 0).
  *   row_offset : 0 for a whole graph.  For a 1-D row shard (multi-GPU) the CSR holds rows
  *              [row_offset, row_offset + n) of the global matrix: `col`, `x` and `dinv` use global
  *              node ids, `y` is local ([n][d]).
@@ -125,7 +124,7 @@ int wdgh_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, i
                   const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                   int norm, int add_self_loop, const float *dinv,
                   const uint8_t *deg_code /* nullable: from wdgh_degree_scale, global ids like dinv */,
-                  const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                  int64_t *plan_i64, const int64_t *plan_host, float *partial,
                   int64_t row_offset, void *stream);
 
 /* ---- phased aggregation (overlap of the feature all-gather with compute, N > 1) ---- */
@@ -140,21 +139,21 @@ int wdgh_plan_heavy_flags(const int64_t *plan_i64, const int64_t *plan_host, int
  *   accumulate != 0 : y += (instead of y =);   finalize != 0 : apply the self loop and the row scale now
  *   (earlier phases store raw partial sums);   run_split_rows != 0 : afterwards compute the split rows over their
  *   full column range (they need all of x; finalized or raw like the call).
+ *   extra_parts_host : HOST array of n_extra (<= 8) device pointers to raw partial sums of the SAME rows
+ *   (float32[n][ld_extra], local row index like y), added to every row as it is stored -- the partial of an earlier
+ *   column range kept in another buffer and, in the 2-D multi-GPU partition, the row slices the peers stored into
+ *   this rank's memory over NVLink: the last phase of a row slice is also its reduction + epilogue.  The split-row
+ *   pass adds only the LAST n_extra_split of them (an earlier phase never stores split rows).  Needs d >= 128.
+ *   `y` (and the extra parts) may be peer-mapped memory of another GPU.
  * Needs 16-byte aligned rows and d in {32, 64} or d >= 128. */
 int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, const int64_t *range_end,
                          const int32_t *col, const float *val, int64_t n,
                          const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                          int norm, int add_self_loop, const float *dinv, const uint8_t *deg_code,
                          const uint8_t *skip_rows, int accumulate, int finalize, int run_split_rows,
-                         const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                         const float *const *extra_parts_host, int32_t n_extra, int32_t n_extra_split, int64_t ld_extra,
+                         int64_t *plan_i64, const int64_t *plan_host, float *partial,
                          int64_t row_offset, void *stream);
-
-/* 2-D partition epilogue: y[r] = s_r * (sum_p parts[p][r] + [self loop] t_r * x[r + row_offset]) for `rows` rows, where
- * parts are raw partial aggregations (wdgh_spmm_csr_ranged with finalize = 0) of the same rows over disjoint column
- * groups (own partial + slices pulled from peers).  parts_host: HOST array of n_parts (<= 16) device pointers. */
-int wdgh_reduce_finalize(const float *const *parts_host, int32_t n_parts, int64_t rows, int64_t d, int64_t ld_parts,
-                         const float *x, int64_t ldx, float *y, int64_t ldy,
-                         int norm, int add_self_loop, const float *dinv, int64_t row_offset, void *stream);
 
 /* ---- label metrics: one pass over the edges ------------------------------ */
 /* Integer statistics every label metric of homophily_metrics.py is a ratio of
@@ -188,7 +187,7 @@ int wdgh_reduce_finalize(const float *const *parts_host, int32_t n_parts, int64_
 #define WDGH_SC_WORDS(C)    (WDGH_SC_HEADER + 3 * (C) + (C) * (C))
 int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                           const int32_t *labels, int32_t num_classes,
-                          const int64_t *plan_i64, const int64_t *plan_host,
+                          int64_t *plan_i64, const int64_t *plan_host,
                           int64_t *counters, double *node_sum,
                           int32_t *deg_nsl, int32_t *match_nsl,
                           uint8_t *labels_u8_scratch /* nullable: uint8[n_labels]; when given and C <= 254 the
@@ -196,19 +195,15 @@ int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, 
                           int64_t n_labels /* length of `labels` (= n for a whole graph, n_global for a shard) */,
                           int64_t row_offset /* as in wdgh_spmm_csr: labels are global, deg/match local */,
                           void *stream);
-/* A_hat X aggregation AND the label statistics in one call (binary adjacency): the union of
- * wdgh_spmm_csr and wdgh_structure_counts, same arguments, same results (Y bit-identical, counters
- * exact).  single_kernel != 0 (and d % 4 == 0, d >= 128, C <= 64, labels_u8_scratch given) folds the
- * per-entry label work into the aggregation kernel; single_kernel == 0 runs the two passes back to
- * back, which is the faster form on the B200 and the default of the host mirror. */
+/* A_hat X aggregation AND the label statistics in one call (binary adjacency): wdgh_spmm_csr followed by
+ * wdgh_structure_counts on the same stream, same arguments, same results. */
 int wdgh_spmm_structure_fused(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
                               const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                               int norm, int add_self_loop, const float *dinv, const uint8_t *deg_code,
                               const int32_t *labels, int32_t num_classes,
-                              const int64_t *plan_i64, const int64_t *plan_host, float *partial,
+                              int64_t *plan_i64, const int64_t *plan_host, float *partial,
                               int64_t *counters, double *node_sum, int32_t *deg_nsl, int32_t *match_nsl,
-                              uint8_t *labels_u8_scratch, int64_t n_labels, int64_t row_offset,
-                              int single_kernel, void *stream);
+                              uint8_t *labels_u8_scratch, int64_t n_labels, int64_t row_offset, void *stream);
 /* Same statistics from an arbitrary edge list (torch `edge_index` int64[2][E]: unsorted, repeats
  * counted with multiplicity), as node_homophily_edge_idx / compact_matrix_edge_idx / our_measure
  * receive it (hm.py:71,81,105).  Row lengths are unknown here, so the per-class degree mass
@@ -240,12 +235,18 @@ int wdgh_edge_cosine(const int64_t *rowptr, const int32_t *col, const float *val
 
 /* ---- dense contractions: aggregation similarity and the KR Gram ---------- */
 /* g[m][m] = z z^T for z float32[m][d]  ((A X)(A X)^T, hm.py:192,199-200,234-235,246).
- * use_tensor_cores != 0: TMA-fed tcgen05 kernel, 3xTF32 operand split (fp32-level accuracy), fp32
- *   accumulation in TMEM; needs `workspace` = float32[wdgh_gram_workspace_floats(m, d)], 16-byte aligned.
- * use_tensor_cores == 0: SIMT fp32 tile kernel (cross-check), workspace may be NULL. */
+ *   mode WDGH_GRAM_TC / WDGH_GRAM_TC_FAITHFUL: TMA-fed tcgen05 kernel, 3xTF32 operand split (fp32-level products),
+ *     128 x 256 tiles, upper triangle only; the k-blocks are accumulated in TMEM in chunks that the epilogue warps add in
+ *     fp32 registers: 4 k-blocks per chunk (TC, ~5e-7 relative) or 1 (TC_FAITHFUL, fp32 level: the KR metric feeds the
+ *     Gram to pinv(rcond=1e-15), which amplifies rounding noise).  Needs `workspace` =
+ *     float32[wdgh_gram_workspace_floats(m, d)], 16-byte aligned.  d <= 32 is routed to the SIMT kernel (faster there).
+ *   mode WDGH_GRAM_SIMT: SIMT fp32 tile kernel (cross-check), workspace may be NULL. */
+#define WDGH_GRAM_SIMT        0
+#define WDGH_GRAM_TC          1
+#define WDGH_GRAM_TC_FAITHFUL 2
 int64_t wdgh_gram_workspace_floats(int64_t m, int64_t d);
 int wdgh_gram(const float *z, int64_t m, int64_t d, int64_t ldz,
-              float *g, int64_t ldg, int use_tensor_cores, float *workspace, void *stream);
+              float *g, int64_t ldg, int mode, float *workspace, void *stream);
 /* gather rows: out[k][:] = x[ids[k]][:]  (torch indexing `[sample, :]`, hm.py:199,234,246) */
 int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const int64_t *ids, int64_t m,
                      float *out, int64_t ldo, void *stream);

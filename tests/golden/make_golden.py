@@ -33,34 +33,36 @@ REF = "/root/reference"
 
 
 # --------------------------------------------------------------------------
-# stubs for dependencies that are not installed (none is on the hot path)
+# the unmodified reference, imported through oracle/ref_shim.py (stubs for the absent third-party imports only)
 # --------------------------------------------------------------------------
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_shim  # noqa: E402
 
-
-def _scatter_add(src, index, dim=-1, out=None, dim_size=None):
-    assert out is not None
-    return out.scatter_add_(dim, index, src)
-
-
-_stub("torch_scatter", scatter_add=_scatter_add)
-_stub("dgl")
-_tg = _stub("torch_geometric")
-_tg.utils = _stub("torch_geometric.utils", to_undirected=None)
-_stub("google_drive_downloader", GoogleDriveDownloader=object)
-_stub("ogb")
-_stub("ogb.nodeproppred", NodePropPredDataset=object)
-
-sys.path.insert(0, REF)
 _cwd = os.getcwd()
 os.chdir(REF)  # the reference opens "data/ind.cora.x" relative to its root
-import utils.homophily_metrics as hm  # noqa: E402
-import utils.homophily_plot as hp  # noqa: E402  (dense-adjacency variants used by synthetic_plot.py)
-import utils.util_funcs as uf  # noqa: E402
+hm, uf, hp = ref_shim.load(REF)
+np.int = int  # utils/datasets.py:109 still says `np.int` (removed in numpy 1.24); an alias, not a patch of the reference
+import utils.datasets as ds  # noqa: E402  (load_fb100_dataset for the LINKX fixtures; resolved by the shim's sys.modules)
+from sklearn.preprocessing import label_binarize as _label_binarize  # noqa: E402
+ds.label_binarize = _label_binarize  # datasets.py:118 calls it without importing it (LINKX's own file does import it)
+
+
+class capture_kr_epochs:
+    """Records the per-epoch accuracy vectors the reference hands to scipy's t-test (hm.py:340): the p-value is a
+    function of them, and they are what a flipped validation prediction changes."""
+
+    def __init__(self, mod):
+        self.mod, self.real, self.x, self.g = mod, mod.ttest_ind, None, None
+
+    def __enter__(self):
+        def spy(a, b, *args, **kw):
+            self.x, self.g = np.asarray(a, dtype=np.float64).copy(), np.asarray(b, dtype=np.float64).copy()
+            return self.real(a, b, *args, **kw)
+        self.mod.ttest_ind = spy
+        return self
+
+    def __exit__(self, *exc):
+        self.mod.ttest_ind = self.real
 
 
 def seed_all(s):
@@ -156,9 +158,11 @@ def gram_metrics(adj_spmm, features, labels, out, sample_n, tag=""):
 def kr_metric(adj_spmm, features, labels, out, sample_max, epochs, tag=""):
     for clf in ("kernel_reg0", "kernel_reg1", "gnb"):
         seed_all(2023)
-        p, _ = hm.classifier_based_performance_metric(features, adj_spmm, labels, sample_max,
-                                                      base_classifier=clf, epochs=epochs)
+        with capture_kr_epochs(hm) as cap:
+            p, _ = hm.classifier_based_performance_metric(features, adj_spmm, labels, sample_max,
+                                                          base_classifier=clf, epochs=epochs)
         out[f"out_kr_p_{clf}{tag}"] = np.float64(p)
+        out[f"out_kr_acc_x_{clf}{tag}"], out[f"out_kr_acc_g_{clf}{tag}"] = cap.x, cap.g
     out[f"in_kr_sample_max{tag}"] = np.int64(sample_max)
     out[f"in_kr_epochs{tag}"] = np.int64(epochs)
     out[f"in_kr_seed{tag}"] = np.int64(2023)
@@ -386,8 +390,10 @@ def case_plot_variants():
         out["out_compat"] = t2n(hp.compact_matrix_edge_idx(ei_t, labels))
         for clf in ("kernel_reg0", "kernel_reg1", "gnb"):
             seed_all(77)
-            out[f"out_kr_p_{clf}"] = np.float64(hp.classifier_based_performance_metric(
-                features, adj, labels, sample_max=300, base_classifier=clf, epochs=4))
+            with capture_kr_epochs(hp) as cap:
+                out[f"out_kr_p_{clf}"] = np.float64(hp.classifier_based_performance_metric(
+                    features, adj, labels, sample_max=300, base_classifier=clf, epochs=4))
+            out[f"out_kr_acc_x_{clf}"], out[f"out_kr_acc_g_{clf}"] = cap.x, cap.g
         out["in_kr"] = np.array([77, 300, 4], dtype=np.int64)  # seed, sample_max, epochs
         save(f"plot_syn_{nedge}_{h}_{s}", **out)
 
@@ -433,9 +439,66 @@ def case_util_norm():
     save("util_norm", **out)
 
 
+# --------------------------------------------------------------------------
+# case 6: the LINKX-family graphs the reference ships (data/facebook100/*.mat) through ITS loader
+# (utils/datasets.py:105-128 load_fb100_dataset: gender label, 0 -> -1 = unlabelled; one-hot features) and the
+# large-dataset flow of homophily_tests.py:88-137 (f.normalize(p=1), sys_/row_normalized_adjacency, metric dispatch,
+# 10 x similarity on class-balanced samples, KR).  `to_undirected` (torch_geometric, util_funcs.py:239) is a no-op on
+# these symmetric matrices up to coalescing, which `sparse_coo_tensor(...).coalesce()` does here.
+# --------------------------------------------------------------------------
+def case_linkx():
+    import torch.nn.functional as f
+    for fname, kr_sample_max, num_sample in (("Reed98", 300, 10000), ("Amherst41", 400, 1000),
+                                             ("Johns Hopkins55", 500, 2000), ("Cornell5", 500, 10000)):
+        dataset = ds.load_fb100_dataset(fname)
+        ei = dataset.graph["edge_index"]
+        n = int(dataset.graph["num_nodes"])
+        und = torch.sparse_coo_tensor(torch.cat([ei, ei.flip(0)], 1), torch.ones(2 * ei.shape[1]), (n, n)).coalesce()
+        row, col = t2n(und.indices())
+        adj_sp = sp.coo_matrix((np.ones(row.shape[0]), (row, col)), shape=(n, n))          # uf.py:242
+        features_raw, labels = dataset.graph["node_feat"], dataset.label.long()
+        A = uf.sparse_mx_to_torch_sparse_tensor(adj_sp).coalesce()                         # uf.py:357
+        big = fname == "Cornell5"
+        out = {"in_n": np.int64(n), "in_labels": t2n(labels).astype(np.int64),
+               "in_features": t2n(features_raw).astype(np.uint8), "in_num_sample": np.int64(num_sample)}
+        up = row < col                                                                     # symmetric: store one triangle
+        out["in_edges_upper"] = np.vstack([row[up], col[up]]).astype(np.int32)
+        assert 2 * int(up.sum()) == row.shape[0]
+        features = f.normalize(features_raw, p=1, dim=1)                                   # homophily_tests.py:95
+        out["out_features_l1"] = t2n(features[:: max(1, n // 64)])
+        for sym, fn in ((1, uf.sys_normalized_adjacency), (0, uf.row_normalized_adjacency)):
+            adjn = uf.sparse_mx_to_torch_sparse_tensor(fn(adj_sp)).coalesce()              # :98-104
+            o = {}
+            structure_metrics(adjn, labels, o)                                             # :108-116 metric dispatch
+            o["out_adj_values_sum"] = np.float64(adjn.values().double().sum())
+            o["out_adj_values_head"] = t2n(adjn.values()[:4096])
+            seed_all(3)
+            o["out_gen_edge_homo"] = np.float64(hm.generalized_edge_homophily(adjn, features, labels))  # :117-118
+            spmm_projection(adjn, features, o, "norm")                                     # SGC-1 propagation
+            for k, v in o.items():
+                out[f"{k}__sym{sym}"] = v
+        # aggregation homophily: 10 x similarity on samples (homophily_tests.py:119-132)
+        label_onehot = torch.eye(int(labels.max()) + 1)[labels]
+        for hard, key in ((None, "soft"), (1, "hard")):
+            seed_all(19)
+            las = np.zeros(10)
+            for i in range(10):
+                if n >= num_sample:
+                    idx_train, _, _ = uf.random_disassortative_splits(labels, labels.max() + 1, num_sample / n)
+                else:
+                    idx_train = None
+                las[i] = 2 * float(hm.similarity(label_onehot, A, label_onehot, hard=hard, LP=1, idx_train=idx_train)) - 1
+            out[f"out_agg_homo_{key}_las"] = las
+        out["in_agg_seed"] = np.int64(19)
+        # KR (homophily_tests.py:133-137), few epochs
+        if not big:
+            kr_metric(A, features_raw, labels, out, sample_max=kr_sample_max, epochs=4)
+        save("linkx_" + fname.replace(" ", "_"), **out)
+
+
 if __name__ == "__main__":
     cases = {"plot": case_plot_variants, "cora": case_cora, "datasets": case_datasets, "synthetic": case_synthetic,
-             "edge": case_edge_cases, "util_norm": case_util_norm}
+             "edge": case_edge_cases, "util_norm": case_util_norm, "linkx": case_linkx}
     for name in (sys.argv[1:] or list(cases)):     # no argument = regenerate everything
         cases[name]()
     os.chdir(_cwd)

@@ -371,9 +371,8 @@ def test_fused_pass_equals_separate_passes(W, d, c):
     lab32, mx = W.graph.pack_labels(torch.from_numpy(labels))
     y_ref = W.spmm(g, x, W.NORM_SYM, True)
     s_ref = W.graph.structure_counts(g, lab32, c)
-    for single in (True, False):
-        y, (counters, node_sum, deg, match, _) = W.graph.spmm_structure_fused(g, x, lab32, c, W.NORM_SYM, True,
-                                                                              single_kernel=single)
+    for _ in range(2):   # twice: the plan-resident ticket counters must have re-armed themselves
+        y, (counters, node_sum, deg, match, _) = W.graph.spmm_structure_fused(g, x, lab32, c, W.NORM_SYM, True)
         s = W.graph._unpack_counts(g.n, g.nnz, c, counters, node_sum, deg, match)
         assert torch.equal(y, y_ref)
         assert (s.match_all, s.match_lab, s.n_lab, s.n_self, s.n_empty, s.nbins, s.n_nodes_nsl) == \
@@ -587,10 +586,13 @@ def test_phased_aggregation_equals_one_pass(W, d, parts):
         assert err <= 1e-5 * y_ref.abs().max().item(), (r, err)
 
 
-@pytest.mark.parametrize("d,world,n", [(128, 4, 20000), (64, 8, 20003)])
-def test_2d_partition_blocks_reduce_to_one_pass(W, d, world, n):
-    """Single-GPU replay of the 2-D partition: every rank's block as raw partial sums per row slice
-    (wdgh_spmm_csr_ranged, finalize=0, split rows included), then wdgh_reduce_finalize at the owner == one SpMM."""
+@pytest.mark.parametrize("d,world,n", [(128, 4, 20000), (256, 8, 20003), (128, 2, 9001)])
+def test_2d_partition_replay_on_one_gpu(W, d, world, n):
+    """Single-GPU replay of Cuda2DShardedStats' arithmetic for every owner rank: foreign producers aggregate the
+    owner's row slice over their column group as raw partial sums (what their kernels store into the owner's receive
+    slots); the owner aggregates its slice over its own shard's columns into slot 0 and finishes with the partner
+    shard's columns + all slots + self loop + scale in ONE ranged launch (extra partial sums) == one SpMM.
+    Every producer sees NaN outside the two feature shards of its column group."""
     from wdgh_b200.sharded import Grid2D
     row, col, _ = powerlaw_graph(n, 10, seed=d)
     keep = row != col
@@ -613,8 +615,10 @@ def test_2d_partition_blocks_reduce_to_one_pass(W, d, world, n):
     for owner in range(world):
         r0, r1 = grid.part.bounds(owner)
         i, s = grid.coords(owner)
-        parts = []
+        slots = [None] * pc
+        own = None
         for j in range(pc):     # producer rank (i, j): rows of `owner`, columns of column group j
+            prod = i * pc + j
             lo, hi = rowptr[r0], rowptr[r1]
             c_s = colg[lo:hi]
             rid = np.repeat(np.arange(r1 - r0), np.diff(rowptr[r0:r1 + 1]))
@@ -625,31 +629,28 @@ def test_2d_partition_blocks_reduce_to_one_pass(W, d, world, n):
                             row_offset=r0, n_global=n, threshold=64)
             n_heavy += sg.n_heavy
             skip = W.graph.heavy_flags(sg) if sg.n_chunks else None
-            # degree codes are optional for the ranged entry: exercise both forms
-            dcode = code_pad if world == 8 else None
-            part = torch.full((blk, d), float("nan"), device="cuda")
-            W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_pad, part, W.NORM_SYM, True, dinv_pad, dcode, skip,
-                                False, False, True)
-            parts.append(part)
-            if owner in (1, world - 2):
-                # WDGH_2D_SPLIT_FIRST: the same slice in phases -- the producer's own-shard columns first, then the
-                # partner shards' columns below / above them with `y +=`, split rows with the last phase
-                prod = i * pc + j
-                seg = W.graph.column_segments(sg, [prod * blk, (prod + 1) * blk])
-                split = torch.full((blk, d), float("nan"), device="cuda")
-                W.graph.spmm_ranged(sg, seg[0], seg[1], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode, skip,
-                                    False, False, False)
-                below, above = i > 0, i < grid.pr - 1
-                if below:
-                    W.graph.spmm_ranged(sg, sg.rowptr[:-1], seg[0], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode,
-                                        skip, True, False, not above)
-                if above:
-                    W.graph.spmm_ranged(sg, seg[1], sg.rowptr[1:], x_pad, split, W.NORM_SYM, True, dinv_pad, dcode,
-                                        skip, True, False, True)
-                rows_s = r1 - r0
-                assert (split[:rows_s] - part[:rows_s]).abs().max().item() <= 1e-5 * part[:rows_s].abs().max().item()
-        y = torch.empty((r1 - r0, d), device="cuda")
-        W.graph.reduce_finalize(parts, x_pad, y, W.NORM_SYM, True, dinv_pad, r0)
+            dcode = code_pad if world != 4 else None    # degree codes are optional for the ranged entry
+            x_cols = torch.full((n_pad, d), float("nan"), device="cuda")
+            for src in grid.col_group_ranks(j):
+                x_cols[src * blk:(src + 1) * blk] = x_pad[src * blk:(src + 1) * blk]
+            if prod != owner:
+                k = (s - j) % pc
+                assert grid.slot_source(owner, k) == prod and (k, s, owner) in grid.schedule(prod)
+                part = torch.full((blk, d), float("nan"), device="cuda")
+                W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_cols, part, W.NORM_SYM, True, dinv_pad, dcode,
+                                    skip, False, False, True)
+                slots[k] = part
+            else:
+                own = (sg, skip, dcode, x_cols)
+        sg, skip, dcode, x_cols = own
+        seg = W.graph.column_segments(sg, [owner * blk, (owner + 1) * blk])
+        slots[0] = torch.full((blk, d), float("nan"), device="cuda")
+        W.graph.spmm_ranged(sg, seg[0], seg[1], x_cols, slots[0], W.NORM_SYM, True, dinv_pad, dcode, skip,
+                            False, False, False)
+        rb, re = (sg.rowptr[:-1], seg[0]) if i == 1 else (seg[1], sg.rowptr[1:])
+        y = torch.full((r1 - r0, d), float("nan"), device="cuda")
+        W.graph.spmm_ranged(sg, rb, re, x_cols, y, W.NORM_SYM, True, dinv_pad, dcode, skip, False, True, True,
+                            extra=slots, extra_split=pc - 1)
         err = (y - y_ref[r0:r1]).abs().max().item()
         assert err <= 1e-5 * y_ref.abs().max().item(), (owner, err)
     assert n_heavy > 0

@@ -28,7 +28,7 @@ def sgc1_propagate(adj, x):
     assert lib.wdgh_coo_to_csr(adj.indices().data_ptr(), nnz, n, rowptr.data_ptr(), col.data_ptr(), st) == 0
     # degree binning plan: rows longer than 512 entries are split (capacity >= 2*nnz/512 + 2)
     cap = 2 * nnz // 512 + 2
-    plan = torch.empty(8 + 3 * cap + (nnz + 1023) // 1024, dtype=torch.int64, device=dev)   # WDGH_PLAN_WORDS
+    plan = torch.empty(16 + 3 * cap, dtype=torch.int64, device=dev)                        # WDGH_PLAN_WORDS(cap)
     plan_host = (i64 * 8)()
     assert lib.wdgh_plan_build(rowptr.data_ptr(), n, nnz, 512, plan.data_ptr(), cap, plan_host, st) == 0
     # D^-1/2 of A + I (float scale + 1-byte degree codes)

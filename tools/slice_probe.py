@@ -3,8 +3,7 @@ column group, ~5 stored entries per row) aggregated as raw partial sums, next to
 
     python tools/slice_probe.py [--world 8] [--nodes 50000000]
 
-Prints one JSON line per case: kernel time and algorithmic GB/s.  Kernel variants are chosen with the library's
-environment knobs (WDGH_ROWGROUP, WDGH_PIPE_MINB)."""
+Prints one JSON line per case: kernel time and algorithmic GB/s."""
 import argparse
 import json
 import os
@@ -54,7 +53,7 @@ def main():
     code_f = torch.zeros(world * blk, dtype=torch.uint8, device=dev)
     dinv_f[r0:r1], code_f[r0:r1] = dinv, code
     y = torch.empty((blk, d), dtype=torch.float32, device=dev)
-    out = {"env": {k: os.environ.get(k) for k in ("WDGH_ROWGROUP", "WDGH_PIPE_MINB")}}
+    out = {}
     ms = timed(lambda: G.spmm(g1, x, W.NORM_SYM, True, out=y[:g1.n], dinv=dinv_f, deg_code=code_f))
     by = g1.nnz * (8 + 4 * d) + g1.n * (12 + 8 * d)
     out["shard_1d"] = {"rows": g1.n, "entries": g1.nnz, "ms": round(ms, 3), "GBps": round(by / ms / 1e6, 1)}

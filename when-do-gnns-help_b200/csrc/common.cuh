@@ -44,9 +44,6 @@ inline int fail_cuda(cudaError_t e, const char *where) {
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached multiProcessorCount of the current device
-// Zeroed 64-bit ticket counter for one launch of a row-group kernel (memset ordered on `st`).  One ring of 64 slots per
-// device, handed out round-robin: up to 64 launches may be in flight per device.  nullptr on allocation failure.
-unsigned long long *ticket_slot(cudaStream_t st);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -100,13 +97,16 @@ constexpr int kPlanNHeavy = 0;      // number of split rows
 constexpr int kPlanNChunks = 1;     // number of chunks over all split rows
 constexpr int kPlanThreshold = 2;   // heavy threshold (entries)
 constexpr int kPlanCapacity = 3;    // capacity (chunks) of the three arrays below
-constexpr int kPlanUnit = 4;        // entries per stream unit (WDGH_UNIT)
-constexpr int kPlanNUnits = 5;      // number of stream units = ceil(nnz / unit)
+// Scheduling words of the persistent row-group kernels: a 64-bit ticket counter (groups handed out so far) and a
+// count of finished CTAs.  Zeroed by wdgh_plan_build; the last CTA of a launch zeroes both again, so no memset is
+// needed between launches.  One pair per kernel family: a plan must not be used by two launches that run
+// concurrently (they would also share the split-row `partial` scratch).
+constexpr int kPlanSpmmTicket = 8;   // [8] tickets, [9] finished CTAs of spmm_rowgroup_kernel
+constexpr int kPlanLabelTicket = 10; // [10] tickets, [11] finished CTAs of the label edge pass
 // arrays after the header, each `capacity` long:
 //   heavy_row[k]      row id of split row k
 //   heavy_chunk0[k]   first chunk id of split row k
 //   chunk_owner[c]    split-row index k that owns chunk c
-// followed by unit_row[u] (n_units long): the row that contains stored entry u * unit
 __host__ __device__ inline const int64_t *plan_heavy_row(const int64_t *p) { return p + WDGH_PLAN_HEADER; }
 __host__ __device__ inline const int64_t *plan_heavy_chunk0(const int64_t *p, int64_t cap) {
   return p + WDGH_PLAN_HEADER + cap;
@@ -114,8 +114,21 @@ __host__ __device__ inline const int64_t *plan_heavy_chunk0(const int64_t *p, in
 __host__ __device__ inline const int64_t *plan_chunk_owner(const int64_t *p, int64_t cap) {
   return p + WDGH_PLAN_HEADER + 2 * cap;
 }
-__host__ __device__ inline const int64_t *plan_unit_row(const int64_t *p, int64_t cap) {
-  return p + WDGH_PLAN_HEADER + 3 * cap;
+inline unsigned long long *plan_sched(int64_t *plan, int word) {
+  return reinterpret_cast<unsigned long long *>(plan + word);
+}
+
+// Ticket dispenser of a persistent row-group kernel.  `sched[0]` counts tickets, `sched[1]` finished CTAs.
+// retire(): every CTA calls it once after its last ticket; the CTA that finishes last re-arms both words.
+__device__ __forceinline__ void sched_retire(unsigned long long *sched, unsigned total_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(&sched[1], 1ull);
+    if (done == (unsigned long long)total_ctas - 1ull) {
+      atomicExch(&sched[0], 0ull);
+      atomicExch(&sched[1], 0ull);
+    }
+  }
 }
 
 }  // namespace wdgh

@@ -283,7 +283,7 @@ edge_cosine_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
 using namespace wdgh;
 
 int wdgh_gram_tc_launch(const float *z, int64_t m, int64_t d, int64_t ldz, float *g, int64_t ldg, float *workspace,
-                        cudaStream_t st);
+                        int chunk, cudaStream_t st);
 
 extern "C" int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const int64_t *ids, int64_t m, float *out,
                                 int64_t ldo, void *stream) {
@@ -295,11 +295,16 @@ extern "C" int wdgh_gather_rows(const float *x, int64_t d, int64_t ldx, const in
 }
 
 extern "C" int wdgh_gram(const float *z, int64_t m, int64_t d, int64_t ldz, float *g, int64_t ldg,
-                         int use_tensor_cores, float *workspace, void *stream) {
+                         int mode, float *workspace, void *stream) {
   WDGH_REQUIRE(z && g && m >= 0 && d >= 1 && ldz >= d && ldg >= m, "wdgh_gram: bad arguments");
+  WDGH_REQUIRE(mode == WDGH_GRAM_SIMT || mode == WDGH_GRAM_TC || mode == WDGH_GRAM_TC_FAITHFUL, "wdgh_gram: bad mode");
   if (m == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (use_tensor_cores) return wdgh_gram_tc_launch(z, m, d, ldz, g, ldg, workspace, st);
+  // K <= 32 (the similarity of one-hot labels, homophily_tests.py:131): a single k-block cannot feed the tensor
+  // pipe and the 128 x 256 tiles are all epilogue -- the SIMT kernel is faster there (round 1: 0.22 vs 0.46 ms at
+  // m = 10000, d = 10), so the tensor-core modes route it themselves.
+  if (mode != WDGH_GRAM_SIMT && d > 32)
+    return wdgh_gram_tc_launch(z, m, d, ldz, g, ldg, workspace, mode == WDGH_GRAM_TC_FAITHFUL ? 1 : 4, st);
   dim3 grid((unsigned)ceil_div(m, 64), (unsigned)ceil_div(m, 64));
   gram_simt_kernel<<<grid, 256, 0, st>>>(z, m, d, ldz, g, ldg);
   WDGH_LAUNCHED("gram_simt_kernel");

@@ -7,7 +7,6 @@
 #include <limits.h>
 
 #include <atomic>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -26,21 +25,6 @@ int sm_count() {
     cached[dev] = v;
   }
   return cached[dev];
-}
-
-unsigned long long *ticket_slot(cudaStream_t st) {
-  static unsigned long long *ring[64] = {nullptr};
-  static std::atomic<unsigned> next{0};
-  static std::mutex mu;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!ring[dev] && cudaMalloc(&ring[dev], 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-  }
-  unsigned long long *slot = ring[dev] + (next.fetch_add(1) & 63u);
-  if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
-  return slot;
 }
 
 // ---------------------------------------------------------------------------
@@ -146,22 +130,6 @@ __global__ void plan_fill_owner_kernel(const int64_t *__restrict__ rowptr, int64
     const int64_t nch = (rowptr[r + 1] - rowptr[r] + T - 1) / T;
     const int64_t c0 = heavy_chunk0[k];
     for (int64_t p = lane; p < nch; p += 32) owner[c0 + p] = k;
-  }
-}
-
-// unit_row[u] = the row containing stored entry u * unit  (smallest r with rowptr[r+1] > u * unit)
-__global__ void plan_unit_rows_kernel(const int64_t *__restrict__ rowptr, int64_t n, int64_t unit, int64_t n_units,
-                                      int64_t *__restrict__ unit_row) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {
-    const int64_t pos = u * unit;
-    int64_t lo = 0, hi = n;  // invariant: rowptr[lo] <= pos, answer in [lo, hi)
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (rowptr[mid] <= pos) lo = mid;
-      else hi = mid;
-    }
-    unit_row[u] = lo;  // largest r with rowptr[r] <= pos; rowptr[r+1] > pos because pos < nnz
   }
 }
 
@@ -349,8 +317,8 @@ extern "C" int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t nnz, in
   WDGH_REQUIRE(rowptr && plan_i64 && plan_host && n >= 0 && nnz >= 0 && heavy_threshold >= 32 && capacity >= 1,
                "wdgh_plan_build: bad arguments");
   cudaStream_t st = as_stream(stream);
-  const int64_t n_units = ceil_div(nnz, WDGH_UNIT);
-  int64_t hdr[WDGH_PLAN_HEADER] = {0, 0, heavy_threshold, capacity, WDGH_UNIT, n_units, nnz, 0};
+  // header: counters, parameters, and the self-resetting scheduling words (tickets) of the row-group kernels
+  int64_t hdr[WDGH_PLAN_HEADER] = {0, 0, heavy_threshold, capacity, 0, 0, nnz, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   WDGH_CUDA(cudaMemcpyAsync(plan_i64, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
   if (n > 0) {
     plan_find_heavy_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, 0, st>>>(rowptr, n, heavy_threshold,
@@ -359,11 +327,6 @@ extern "C" int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t nnz, in
     plan_fill_owner_kernel<<<persistent_grid(ceil_div(capacity, 8), 4), 256, 0, st>>>(rowptr, heavy_threshold,
                                                                                      capacity, plan_i64);
     WDGH_LAUNCHED("plan_fill_owner_kernel");
-    if (n_units > 0) {
-      plan_unit_rows_kernel<<<persistent_grid(ceil_div(n_units, 256), 8), 256, 0, st>>>(
-          rowptr, n, WDGH_UNIT, n_units, plan_i64 + WDGH_PLAN_HEADER + 3 * capacity);
-      WDGH_LAUNCHED("plan_unit_rows_kernel");
-    }
   }
   WDGH_CUDA(cudaMemcpyAsync(hdr, plan_i64, sizeof(hdr), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaStreamSynchronize(st));
@@ -371,8 +334,8 @@ extern "C" int wdgh_plan_build(const int64_t *rowptr, int64_t n, int64_t nnz, in
   plan_host[1] = hdr[kPlanNChunks];
   plan_host[2] = heavy_threshold;
   plan_host[3] = capacity;
-  plan_host[4] = WDGH_UNIT;
-  plan_host[5] = n_units;
+  plan_host[4] = 0;
+  plan_host[5] = 0;
   plan_host[6] = nnz;
   plan_host[7] = 0;
   if (hdr[kPlanNHeavy] > capacity || hdr[kPlanNChunks] > capacity)

@@ -17,14 +17,4 @@ __device__ __forceinline__ void fold_keys(int key, unsigned *s_hist, unsigned lo
   }
 }
 
-// structure.cu: zero the counters, optionally build the 1-byte label copy (returns it, or nullptr when
-// the int32 labels must be used: C > 254 or no scratch)
-int structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint8_t *labels_u8_scratch, int64_t *counters,
-                      double *node_sum, const uint8_t **labels8_out, cudaStream_t st);
-// structure.cu: split-row chunks + per-node reductions (everything after the per-row edge pass)
-int structure_finish(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels,
-                     const uint8_t *labels8, int C, const int64_t *plan_i64, const int64_t *plan_host,
-                     int64_t *counters, double *node_sum, int32_t *deg_nsl, int32_t *match_nsl, int64_t row_offset,
-                     cudaStream_t st);
-
 }  // namespace wdgh

@@ -11,17 +11,15 @@
 // block's phase is exposed after the copies end.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include <mutex>
 
-extern "C" int wdgh_spmm_csr(const int64_t *, const int32_t *, const float *, int64_t, const float *, int64_t,
-                             int64_t, float *, int64_t, int, int, const float *, const uint8_t *, const int64_t *,
-                             const int64_t *, float *, int64_t, void *);
+#include "common.cuh"
 
 namespace wdgh {
 
 struct HostPipelineCache {
   int64_t n = -1, nnz = -1, d = -1, cap = -1, partial_elems = 0;
-  int C = -1;
+  int C = -1, device = -1;
   int64_t *rowptr = nullptr;
   int32_t *col = nullptr;
   float *x = nullptr, *y = nullptr, *dinv = nullptr, *partial = nullptr;
@@ -44,7 +42,8 @@ struct HostPipelineCache {
     *this = HostPipelineCache();
   }
 };
-static HostPipelineCache g_cache;
+static HostPipelineCache g_cache;  // one cached pipeline per process, guarded by g_cache_mu
+static std::mutex g_cache_mu;
 constexpr int64_t kHostPipelineThreshold = 512;
 
 // feature row blocks of the pipelined copy (1 = copy everything, then compute); WDGH_E2E_CHUNKS overrides
@@ -63,6 +62,7 @@ static int e2e_chunks() {
 using namespace wdgh;
 
 extern "C" int wdgh_pipeline_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
   g_cache.release();
   return 0;
 }
@@ -73,11 +73,14 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
                                   double *node_sum_host) {
   WDGH_REQUIRE(rowptr_host && x_host && labels_host && counters_host && node_sum_host, "wdgh_pipeline_host: null pointer");
   WDGH_REQUIRE(n > 0 && nnz >= 0 && d > 0 && num_classes >= 1 && (col_host || nnz == 0), "wdgh_pipeline_host: bad shape");
+  std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached buffers and streams serve one call at a time
   HostPipelineCache &c = g_cache;
   const int C = num_classes;
+  int device = -1;
+  WDGH_CUDA(cudaGetDevice(&device));
   const size_t n_counters = WDGH_SC_WORDS((size_t)C);
   const int64_t cap = 2 * nnz / kHostPipelineThreshold + 2;
-  if (c.n != n || c.nnz != nnz || c.d != d || c.C != C) {
+  if (c.n != n || c.nnz != nnz || c.d != d || c.C != C || c.device != device) {
     c.release();
     WDGH_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
     WDGH_CUDA(cudaMalloc(&c.rowptr, (n + 1) * sizeof(int64_t)));
@@ -90,7 +93,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMalloc(&c.deg_code, n));
     WDGH_CUDA(cudaMalloc(&c.deg, n * sizeof(int32_t)));
     WDGH_CUDA(cudaMalloc(&c.match, n * sizeof(int32_t)));
-    WDGH_CUDA(cudaMalloc(&c.plan, WDGH_PLAN_WORDS(cap, nnz) * sizeof(int64_t)));
+    WDGH_CUDA(cudaMalloc(&c.plan, WDGH_PLAN_WORDS(cap) * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.counters, n_counters * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.node_sum, 2 * sizeof(double)));
     WDGH_CUDA(cudaStreamCreateWithFlags(&c.st_copy, cudaStreamNonBlocking));
@@ -99,7 +102,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMalloc(&c.seg, (size_t)(e2e_chunks() + 1) * (size_t)n * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.bounds, 65 * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.skip, (size_t)n));
-    c.n = n; c.nnz = nnz; c.d = d; c.C = C; c.cap = cap;
+    c.n = n; c.nnz = nnz; c.d = d; c.C = C; c.cap = cap; c.device = device;
   }
   cudaStream_t st = c.st, sc = c.st_copy;
   const bool ranged_ok = (d % 4 == 0) && (d >= 128 || d == 64 || d == 32);
@@ -126,9 +129,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   int rc = wdgh_plan_build(c.rowptr, n, nnz, kHostPipelineThreshold, c.plan, cap, plan_host, st);
   if (rc) return rc;
   const int64_t ldp = (d + 3) & ~int64_t(3);
-  const char *variant = getenv("WDGH_SPMM_VARIANT");  // the experimental stream variant needs 2 rows per unit
-  const int64_t units2 = (variant && atoi(variant) == 2) ? 2 * plan_host[5] : 0;
-  const int64_t n_part = plan_host[1] > units2 ? plan_host[1] : units2;
+  const int64_t n_part = plan_host[1];
   if (n_part * ldp > c.partial_elems) {
     cudaFree(c.partial);
     c.partial = nullptr;
@@ -161,14 +162,30 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
       WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[k], 0));
       const int last = (k == K - 1);
       rc = wdgh_spmm_csr_ranged(c.rowptr, c.seg + (size_t)k * n, c.seg + (size_t)(k + 1) * n, c.col, nullptr, n, c.x, d,
-                                d, c.y, d, norm, add_self_loop, dinv, code, c.skip, k > 0, last, last, c.plan,
-                                plan_host, c.partial, 0, st);
+                                d, c.y, d, norm, add_self_loop, dinv, code, c.skip, k > 0, last, last, nullptr, 0, 0, 0,
+                                c.plan, plan_host, c.partial, 0, st);
       if (rc) return rc;
     }
   }
+  // Y leaves on the copy stream as soon as the last phase is done; the counters follow on the compute stream
+  if (y_host) {
+    WDGH_CUDA(cudaEventRecord(c.ev_csr, st));
+    WDGH_CUDA(cudaStreamWaitEvent(sc, c.ev_csr, 0));
+    WDGH_CUDA(cudaMemcpyAsync(y_host, c.y, n * d * sizeof(float), cudaMemcpyDeviceToHost, sc));
+  }
   WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (y_host) WDGH_CUDA(cudaMemcpyAsync(y_host, c.y, n * d * sizeof(float), cudaMemcpyDeviceToHost, st));
   WDGH_CUDA(cudaStreamSynchronize(st));
+  if (counters_host[WDGH_SC_N_MULTI_NEG] != 0) {
+    // several distinct negative labels: the 1-byte label copy folds them together, but the reference compares raw
+    // labels (hm.py:51) -- redo the label pass on the int32 labels
+    rc = wdgh_structure_counts(c.rowptr, c.col, n, nnz, c.labels, C, c.plan, plan_host, c.counters, c.node_sum, c.deg,
+                               c.match, nullptr, n, 0, st);
+    if (rc) return rc;
+    WDGH_CUDA(cudaMemcpyAsync(counters_host, c.counters, n_counters * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    WDGH_CUDA(cudaStreamSynchronize(st));
+  }
+  if (y_host) WDGH_CUDA(cudaStreamSynchronize(sc));
   return 0;
 }

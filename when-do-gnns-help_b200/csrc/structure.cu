@@ -10,7 +10,7 @@
 //                class degree mass (hm.py:141), empty rows, bincount length.
 // HBM traffic per entry: 4 B of `col` plus one label gather that is served by L2 whenever the
 // label array (4 B/node) fits its 126 MB.
-#include <stdlib.h>
+#include <limits.h>
 
 #include "internal.cuh"
 
@@ -61,82 +61,6 @@ __device__ __forceinline__ int load_label<uint8_t>(const uint8_t *p, int64_t i) 
   return v == 255 ? -1 : v;
 }
 
-// G lanes per row, 4 entries per lane and iteration (all column ids, then all label gathers, are
-// issued before the first fold), next row's bounds prefetched; persistent grid.  Split (heavy) rows
-// get deg/match = 0 here and are completed by structure_chunks_kernel.
-template <int G, typename L>
-__global__ void __launch_bounds__(256)
-structure_rows_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
-                      const L *__restrict__ labels, int C, int64_t threshold,
-                      unsigned long long *__restrict__ counters, int32_t *__restrict__ deg_nsl,
-                      int32_t *__restrict__ match_nsl, int64_t row_offset) {
-  extern __shared__ unsigned s_hist[];
-  const bool use_smem = (C * C <= kHistSmemBins);
-  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
-  if (use_smem) {
-    for (int b = threadIdx.x; b < C * C; b += blockDim.x) s_hist[b] = 0;
-    __syncthreads();
-  }
-  constexpr int RPW = 32 / G;
-  constexpr int EPL = 4;  // entries per lane per iteration
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G, grp = lane / G;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  EdgeAcc acc;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  auto fetch = [&](int64_t ww, int64_t &s, int64_t &e, int &li) {
-    const int64_t row = ww * RPW + grp;
-    s = 0; e = 0; li = -1;
-    if (row < n) {
-      s = __ldg(rowptr + row);
-      e = __ldg(rowptr + row + 1);
-      if (e - s > threshold) e = s;
-      li = load_label<L>(labels, row + row_offset);
-    }
-  };
-  int64_t s, e, ns, ne;
-  int li, nli;
-  if (w * RPW < n) fetch(w, s, e, li);
-  for (; w * RPW < n; w += nwarps) {
-    const int64_t row = w * RPW + grp;
-    if ((w + nwarps) * RPW < n) fetch(w + nwarps, ns, ne, nli);
-    const int iters = warp_max((int)((e - s + G * EPL - 1) / (G * EPL)));
-    int m_nsl = 0, d_nsl = 0;
-    for (int it = 0; it < iters; ++it) {
-      const int64_t base = s + (int64_t)it * (G * EPL) + gl;
-      int j[EPL], lj[EPL];
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) j[k] = (base + k * G < e) ? __ldg(col + base + k * G) : -1;
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) lj[k] = (j[k] >= 0) ? load_label<L>(labels, j[k]) : -1;
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) {
-        int key = -1;
-        if (j[k] >= 0) visit(row + row_offset, li, j[k], lj[k], C, acc, m_nsl, d_nsl, key);
-        fold_keys(key, s_hist, g_hist, use_smem);
-      }
-    }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-      m_nsl += __shfl_xor_sync(0xffffffffu, m_nsl, o);
-      d_nsl += __shfl_xor_sync(0xffffffffu, d_nsl, o);
-    }
-    if (gl == 0 && row < n) {  // heavy rows: zero, the chunk kernel adds atomically
-      deg_nsl[row] = d_nsl;
-      match_nsl[row] = m_nsl;
-    }
-    s = ns; e = ne; li = nli;
-  }
-  flush(acc, counters);
-  if (use_smem) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < C * C; b += blockDim.x) {
-      const unsigned v = s_hist[b];
-      if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
-    }
-  }
-}
-
 // Row-group form of the edge pass: a warp takes GROUPS of 32 consecutive rows (ticket counter: row lengths are
 // heavy-tailed) and walks the stored entries of a group as one stream, 4 x 32 entries per iteration, so every
 // lane carries an entry whatever the row lengths are (the G-lanes-per-row kernel above idles ~1/3 of its
@@ -150,7 +74,7 @@ structure_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__r
                           const L *__restrict__ labels, int C, int64_t threshold,
                           unsigned long long *__restrict__ counters, int32_t *__restrict__ deg_nsl,
                           int32_t *__restrict__ match_nsl, int64_t row_offset,
-                          unsigned long long *__restrict__ next_group) {
+                          unsigned long long *__restrict__ sched) {
   extern __shared__ unsigned s_hist[];
   __shared__ int s_off[8][2][33];
   __shared__ int64_t s_beg[8][2][32];
@@ -170,7 +94,7 @@ structure_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__r
 
   auto take = [&]() -> int64_t {
     unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(next_group, 1ull);
+    if (lane == 0) t = atomicAdd(&sched[0], 1ull);
     return (int64_t)__shfl_sync(kFull, t, 0) + W;  // the first W groups are handed out by position
   };
   auto load_bounds = [&](int64_t g, int64_t &b, int64_t &e, int &li) {
@@ -313,6 +237,284 @@ structure_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__r
     for (int b = threadIdx.x; b < C * C; b += blockDim.x) {
       const unsigned v = s_hist[b];
       if (v) atomicAdd(&g_hist[b], (unsigned long long)v);
+    }
+  }
+  sched_retire(sched, gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// Stream form of the edge pass -- the default (1-byte labels, (C+1)^2 <= 4096 pair bins).  A warp takes GROUPS of 32
+// consecutive rows from a ticket counter and walks the group's stored entries as one stream, EPL x 32 entries per
+// iteration.  What makes it ~4x cheaper per entry than the row-group kernel above:
+//   * the row of a stream position comes from two warp-wide bit operations instead of a 5-step search per lane:
+//     REDUX.OR builds the mask of rows that START inside a 32-entry slice, a ballot counts the rows that started
+//     before it; rank = count + popc(mask & lanes_le) - 1 indexes a compacted table of the non-empty rows
+//     ({row slot, label, address correction}: one 8-byte shared-memory load);
+//   * ONE pair table over (C+1) x (C+1) label values, unlabelled = C, self loops excluded: the four scalar counters
+//     (matches, labelled matches, labelled entries) are sums over its bins taken once per CTA, so the per-entry
+//     work is a single key fold (__match_any_sync + one shared atomic per distinct key);
+//   * per-row match counts are taken on the OWNER side: lane r intersects the slice's match ballot with the bit
+//     range of its own row -- no run detection, no shared-memory counters;
+//   * the per-node reductions (node homophily sum, class sizes / degree mass, empty rows, bincount length) ride in
+//     the group epilogue, where the row owner has everything in registers -- no second pass over the node arrays.
+// Split rows contribute no entries here (structure_chunks_kernel + structure_heavy_nodes_kernel own them).
+// ---------------------------------------------------------------------------
+constexpr int kStreamEPL = 4;
+__global__ void __launch_bounds__(256, 3)
+structure_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
+                        const uint8_t *__restrict__ labels8, int C, int64_t threshold,
+                        unsigned long long *__restrict__ counters, double *__restrict__ node_sum,
+                        int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl, int64_t row_offset,
+                        unsigned long long *__restrict__ sched) {
+  extern __shared__ unsigned s_dyn[];  // [(C+1)^2] pair table, [C+1] class sizes, [C+1] class degree mass
+  __shared__ int2 s_pack[8][2][32];    // per warp, double buffered: {(row slot << 8) | label, address correction}
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int EPL = kStreamEPL;
+  const int C1 = C + 1;
+  unsigned *s_hist = s_dyn, *s_cnt = s_dyn + C1 * C1, *s_deg = s_cnt + C1;
+  for (int b = threadIdx.x; b < C1 * C1 + 2 * C1; b += blockDim.x) s_dyn[b] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lanes_lt = (1u << lane) - 1u, lanes_le = lanes_lt | (1u << lane);
+  const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_groups = (n + 31) >> 5;
+  unsigned n_self = 0, n_self_lab = 0;                  // warp-uniform
+  double sum = 0.0, sum_self = 0.0;                     // per lane (row owner)
+  unsigned n_nsl = 0, n_empty = 0;
+  long long nbins = 0;
+
+  auto take = [&]() -> int64_t {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(&sched[0], 1ull);
+    return (int64_t)__shfl_sync(kFull, t, 0) + W;  // the first W groups are handed out by position
+  };
+  auto load_bounds = [&](int64_t g, int64_t &b, int64_t &e, int &li) {
+    b = 0;
+    e = 0;
+    li = C;
+    const int64_t r = (g << 5) + lane;
+    if (r < n) {
+      b = __ldg(rowptr + r);
+      e = __ldg(rowptr + r + 1);
+      const int v = __ldg(labels8 + r + row_offset);
+      li = (v == 255) ? C : v;
+    }
+  };
+  // scan the row lengths of a group and publish the compacted row table
+  auto publish = [&](int buf, int64_t b, int64_t e, int li, int &off, int &len, int &total, const int32_t *&cp) {
+    len = (e - b > threshold) ? 0 : (int)(e - b);
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
+    }
+    off = inc - len;
+    total = __shfl_sync(kFull, inc, 31);
+    const int64_t gbeg = __shfl_sync(kFull, b, 0);
+    cp = col + gbeg;
+    const unsigned ne = __ballot_sync(kFull, len > 0);
+    if (len > 0) s_pack[wid][buf][__popc(ne & lanes_lt)] = make_int2((lane << 8) | li, (int)(b - gbeg) - off);
+    __syncwarp();
+  };
+  // column ids and row records of stream positions t0 + 32 k + lane (j = -1: past the end)
+  auto load_cols = [&](int buf, int t0, int total, int off, int len, const int32_t *cp, int (&j)[EPL], int (&pk)[EPL]) {
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      const int tk = t0 + 32 * k;
+      j[k] = -1;
+      pk[k] = 0;
+      if (tk < total) {  // warp-uniform
+        const int rel = off - tk;
+        const unsigned heads = __reduce_or_sync(kFull, (len > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+        const int before = __popc(__ballot_sync(kFull, len > 0 && rel < 0));
+        if (tk + lane < total) {
+          const int2 rec = s_pack[wid][buf][before + __popc(heads & lanes_le) - 1];
+          pk[k] = rec.x;
+          j[k] = __ldg(cp + (tk + lane + rec.y));
+        }
+      }
+    }
+  };
+
+  int64_t g = (int64_t)blockIdx.x * 8 + wid;
+  if (g < n_groups) {
+    int64_t b, e;
+    int li_load, li_cur, li_next = C, dall, n_dall = 0;  // dall: full row length (split rows included)
+    load_bounds(g, b, e, li_load);
+    int buf = 0, off, len, total, n_off = 0, n_len = 0, n_total = 0;
+    const int32_t *cp, *n_cp = col;
+    publish(0, b, e, li_load, off, len, total, cp);
+    dall = (int)(e - b); li_cur = li_load;
+    int64_t gn = take(), gnn = 0;
+    load_bounds(gn, b, e, li_load);
+    int j[EPL], pk[EPL], nj[EPL], npk[EPL];
+    load_cols(0, 0, total, off, len, cp, j, pk);
+    while (true) {
+      bool next_ready = false;
+      int my_match = 0, my_self = 0;
+      auto prefetch = [&](int t0) {
+        if (t0 + 32 * EPL < total) {
+          load_cols(buf, t0 + 32 * EPL, total, off, len, cp, nj, npk);
+        } else {
+          publish(buf ^ 1, b, e, li_load, n_off, n_len, n_total, n_cp);
+          n_dall = (int)(e - b); li_next = li_load;
+          load_cols(buf ^ 1, 0, n_total, n_off, n_len, n_cp, nj, npk);
+          gnn = take();
+          load_bounds(gnn, b, e, li_load);
+          next_ready = true;
+        }
+      };
+      const int grow0 = (int)((g << 5) + row_offset);
+      for (int t0 = 0; t0 < total; t0 += 32 * EPL) {
+        int lj[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) lj[k] = (j[k] >= 0) ? (int)__ldg(labels8 + j[k]) : 255;
+        prefetch(t0);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          const int tk = t0 + 32 * k;
+          if (tk >= total) continue;  // warp-uniform
+          const bool valid = j[k] >= 0;
+          const int lie = pk[k] & 0xff, slot = pk[k] >> 8;
+          const int ljx = (lj[k] == 255) ? C : lj[k];
+          const bool self = valid && (j[k] == grow0 + slot);
+          const bool same = valid && !self && (lie == ljx);
+          fold_keys((valid && !self) ? lie * C1 + ljx : -1, s_hist, nullptr, true);
+          const unsigned m = __ballot_sync(kFull, same), sf = __ballot_sync(kFull, self);
+          // owner side: bits of this slice that belong to my row
+          const int lo = min(max(off - tk, 0), 32), hi = min(max(off + len - tk, 0), 32);
+          const unsigned upto_hi = (hi >= 32) ? kFull : ((1u << hi) - 1u);
+          const unsigned mask = (hi > lo) ? (upto_hi & ~((1u << lo) - 1u)) : 0u;
+          my_match += __popc(m & mask);
+          if (sf) {  // warp-uniform and rare: stored diagonal entries
+            my_self += __popc(sf & mask);
+            n_self += __popc(sf);
+            n_self_lab += __popc(__ballot_sync(kFull, self && lie < C));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          j[k] = nj[k];
+          pk[k] = npk[k];
+        }
+      }
+      if (!next_ready) {  // a group without entries
+        prefetch(0);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+          j[k] = nj[k];
+          pk[k] = npk[k];
+        }
+      }
+      // group epilogue: per-row outputs and the per-node reductions of the rows this warp owns
+      const int64_t r = (g << 5) + lane;
+      if (r < n) {
+        const int deg_all = dall;
+        const bool heavy = deg_all > threshold;
+        const int dn = len - my_self;
+        deg_nsl[r] = heavy ? 0 : dn;       // split rows: zero here, the chunk kernel adds atomically
+        match_nsl[r] = heavy ? 0 : my_match;
+        if (!heavy) {
+          if (dn > 0) {
+            sum += (double)((float)my_match / (float)dn);  // float32 division as torch does (hm.py:77)
+            n_nsl += 1;
+            nbins = max(nbins, (long long)(r + row_offset + 1));  // ticket order: groups do not come in row order
+          }
+          if (deg_all == 0) n_empty += 1;
+          else sum_self += (double)((float)(my_match + my_self) / (float)deg_all);  // homophily_plot.py:92-100
+          if (li_cur < C) {
+            atomicAdd(&s_cnt[li_cur], 1u);
+            atomicAdd(&s_deg[li_cur], (unsigned)deg_all);
+            if (dn == 0) atomicAdd(&counters[WDGH_SC_HEADER + 2 * C + (size_t)C * C + li_cur], 1ull);  // isolated: rare
+          }
+        }
+      }
+      g = gn;
+      gn = gnn;
+      buf ^= 1;
+      off = n_off; len = n_len; total = n_total; cp = n_cp;
+      dall = n_dall; li_cur = li_next;
+      if (g >= n_groups) break;
+    }
+  }
+  // ---- per-warp scalars ----
+  {
+    const double s0 = warp_sum(sum), s1 = warp_sum(sum_self);
+    const long long a0 = warp_sum((long long)n_nsl), a1 = warp_sum((long long)n_empty);
+    long long nbm = nbins;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nbm = max(nbm, __shfl_xor_sync(kFull, nbm, o));
+    if (lane == 0) {
+      if (s0 != 0.0) atomicAdd(node_sum, s0);
+      if (s1 != 0.0) atomicAdd(node_sum + 1, s1);
+      if (a0) atomicAdd(&counters[WDGH_SC_N_NODES_NSL], (unsigned long long)a0);
+      if (a1) atomicAdd(&counters[WDGH_SC_N_EMPTY], (unsigned long long)a1);
+      if (nbm) atomicMax(&counters[WDGH_SC_NBINS], (unsigned long long)nbm);
+      if (n_self) {
+        atomicAdd(&counters[WDGH_SC_N_SELF], (unsigned long long)n_self);
+        atomicAdd(&counters[WDGH_SC_MATCH_ALL], (unsigned long long)n_self);
+      }
+      if (n_self_lab) {
+        atomicAdd(&counters[WDGH_SC_MATCH_LAB], (unsigned long long)n_self_lab);
+        atomicAdd(&counters[WDGH_SC_N_LAB], (unsigned long long)n_self_lab);
+      }
+    }
+  }
+  // ---- per-CTA tables: the pair table also yields the scalar counters ----
+  __syncthreads();
+  unsigned long long *g_cls = counters + WDGH_SC_HEADER;
+  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
+  long long m_all = 0, m_lab = 0, n_lab = 0;
+  for (int bin = threadIdx.x; bin < C1 * C1; bin += blockDim.x) {
+    const unsigned v = s_hist[bin];
+    if (v == 0) continue;
+    const int a = bin / C1, b2 = bin - a * C1;
+    if (a == b2) m_all += v;
+    if (a < C && b2 < C) {
+      n_lab += v;
+      if (a == b2) m_lab += v;
+      atomicAdd(&g_hist[a * C + b2], (unsigned long long)v);
+    }
+  }
+  m_all = warp_sum(m_all);
+  m_lab = warp_sum(m_lab);
+  n_lab = warp_sum(n_lab);
+  if (lane == 0) {
+    if (m_all) atomicAdd(&counters[WDGH_SC_MATCH_ALL], (unsigned long long)m_all);
+    if (m_lab) atomicAdd(&counters[WDGH_SC_MATCH_LAB], (unsigned long long)m_lab);
+    if (n_lab) atomicAdd(&counters[WDGH_SC_N_LAB], (unsigned long long)n_lab);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (s_cnt[c]) atomicAdd(&g_cls[c], (unsigned long long)s_cnt[c]);
+    if (s_deg[c]) atomicAdd(&g_cls[C + c], (unsigned long long)s_deg[c]);
+  }
+  sched_retire(sched, gridDim.x);
+}
+
+// per-node reductions of the split rows, after structure_chunks_kernel completed their counts
+__global__ void structure_heavy_nodes_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ labels,
+                                             int C, const int64_t *__restrict__ plan,
+                                             const int32_t *__restrict__ deg_nsl, const int32_t *__restrict__ match_nsl,
+                                             unsigned long long *__restrict__ counters, double *__restrict__ node_sum,
+                                             int64_t row_offset) {
+  const int64_t n_heavy = plan[kPlanNHeavy];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_heavy; k += stride) {
+    const int64_t i = plan_heavy_row(plan)[k];
+    const int d = deg_nsl[i], m = match_nsl[i];
+    const int64_t deg_all = rowptr[i + 1] - rowptr[i];
+    if (d > 0) {
+      atomicAdd(node_sum, (double)((float)m / (float)d));
+      atomicAdd(&counters[WDGH_SC_N_NODES_NSL], 1ull);
+      atomicMax(&counters[WDGH_SC_NBINS], (unsigned long long)(i + row_offset + 1));
+    }
+    atomicAdd(node_sum + 1, (double)((float)(m + (deg_all - d)) / (float)deg_all));
+    const int l = labels[i + row_offset];
+    if (l >= 0 && l < C) {
+      atomicAdd(&counters[WDGH_SC_HEADER + l], 1ull);
+      atomicAdd(&counters[WDGH_SC_HEADER + C + l], (unsigned long long)deg_all);
+      if (d == 0) atomicAdd(&counters[WDGH_SC_HEADER + 2 * C + (size_t)C * C + l], 1ull);
     }
   }
 }
@@ -505,55 +707,26 @@ label_rows_equal_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
   if (lane == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
 }
 
-template <int G, typename L>
-static int launch_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const L *labels, int C,
-                       int64_t threshold, unsigned long long *counters, int32_t *deg, int32_t *match,
-                       size_t smem, cudaStream_t st, int64_t row_offset) {
-  const int64_t ctas = ceil_div(n, (int64_t)8 * (32 / G));
-  structure_rows_kernel<G, L><<<persistent_grid(ctas, 8), 256, smem, st>>>(rowptr, col, n, labels, C, threshold,
-                                                                          counters, deg, match, row_offset);
-  WDGH_LAUNCHED("structure_rows_kernel");
-  return 0;
-}
-
-// WDGH_LABEL_ROWGROUP: 1 (default) = row-group edge pass (ticket order), 0 = G-lanes-per-row kernel.
-// Measured on the 50M-node / 976M-entry bench graph (whole step, same box): 0 -> 97.6 ms, 1 -> 94.2 ms
-static int label_rowgroup_enabled() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char *e = getenv("WDGH_LABEL_ROWGROUP");
-    cached = e ? (atoi(e) != 0) : 1;
-  }
-  return cached;
-}
-// per-row edge pass for one label representation
+// generic edge pass (int32 labels, or more classes than the shared-memory pair table of the stream kernel holds)
 template <typename L>
-static int launch_edge_rows(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz, const L *labels, int C,
+static int launch_edge_rows(const int64_t *rowptr, const int32_t *col, int64_t n, const L *labels, int C,
                             int64_t threshold, unsigned long long *cnt, int32_t *deg_nsl, int32_t *match_nsl,
-                            size_t hist_smem, cudaStream_t st, int64_t row_offset) {
-  if (label_rowgroup_enabled()) {
-    unsigned long long *tickets = ticket_slot(st);
-    if (tickets == nullptr) return fail_cuda(cudaErrorMemoryAllocation, "structure: ticket counter");
-    const int64_t n_groups = ceil_div(n, 32);
-    structure_rowgroup_kernel<L><<<persistent_grid(ceil_div(n_groups, 8), 4), 256, hist_smem, st>>>(
-        rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, row_offset, tickets);
-    WDGH_LAUNCHED("structure_rowgroup_kernel");
-    return 0;
-  }
-  const double avg = (double)nnz / (double)n;
-  // 4 entries per lane and iteration: pick G so that one iteration covers a typical row
-  if (avg <= 16.0) return launch_rows<4, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  if (avg <= 48.0) return launch_rows<8, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  if (avg <= 96.0) return launch_rows<16, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  return launch_rows<32, L>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+                            size_t hist_smem, cudaStream_t st, int64_t row_offset, unsigned long long *sched) {
+  const int64_t n_groups = ceil_div(n, 32);
+  structure_rowgroup_kernel<L><<<persistent_grid(ceil_div(n_groups, 8), 4), 256, hist_smem, st>>>(
+      rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, row_offset, sched);
+  WDGH_LAUNCHED("structure_rowgroup_kernel");
+  return 0;
 }
 
 }  // namespace wdgh
 
 using namespace wdgh;
 
-int wdgh::structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint8_t *labels_u8_scratch,
-                            int64_t *counters, double *node_sum, const uint8_t **labels8_out, cudaStream_t st) {
+// zero the counters, optionally build the 1-byte label copy (returns it, or nullptr when the int32 labels must be
+// used: C > 254 or no scratch)
+static int structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint8_t *labels_u8_scratch,
+                             int64_t *counters, double *node_sum, const uint8_t **labels8_out, cudaStream_t st) {
   const size_t n_counters = WDGH_SC_WORDS((size_t)C);
   WDGH_CUDA(cudaMemsetAsync(counters, 0, n_counters * sizeof(int64_t), st));
   WDGH_CUDA(cudaMemsetAsync(node_sum, 0, 2 * sizeof(double), st));
@@ -567,32 +740,8 @@ int wdgh::structure_prepare(const int32_t *labels, int64_t n_labels, int C, uint
   return 0;
 }
 
-int wdgh::structure_finish(const int64_t *rowptr, const int32_t *col, int64_t n, const int32_t *labels,
-                           const uint8_t *labels8, int C, const int64_t *plan_i64, const int64_t *plan_host,
-                           int64_t *counters, double *node_sum, int32_t *deg_nsl, int32_t *match_nsl,
-                           int64_t row_offset, cudaStream_t st) {
-  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
-  const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
-  const int64_t n_chunks = plan_host[1];
-  if (n_chunks > 0) {
-    const unsigned grid = persistent_grid(ceil_div(n_chunks, 8), 8);
-    if (labels8)
-      structure_chunks_kernel<uint8_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels8, C, plan_i64, n_chunks, cnt,
-                                                                    deg_nsl, match_nsl, row_offset);
-    else
-      structure_chunks_kernel<int32_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels, C, plan_i64, n_chunks, cnt,
-                                                                    deg_nsl, match_nsl, row_offset);
-    WDGH_LAUNCHED("structure_chunks_kernel");
-  }
-  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
-  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
-                                                                                     match_nsl, cnt, node_sum, row_offset);
-  WDGH_LAUNCHED("structure_nodes_kernel");
-  return 0;
-}
-
 extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, int64_t n, int64_t nnz,
-                                     const int32_t *labels, int32_t num_classes, const int64_t *plan_i64,
+                                     const int32_t *labels, int32_t num_classes, int64_t *plan_i64,
                                      const int64_t *plan_host, int64_t *counters, double *node_sum,
                                      int32_t *deg_nsl, int32_t *match_nsl, uint8_t *labels_u8_scratch,
                                      int64_t n_labels, int64_t row_offset, void *stream) {
@@ -607,13 +756,49 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   int rc = structure_prepare(labels, n == 0 ? 0 : n_labels, C, labels_u8_scratch, counters, node_sum, &labels8, st);
   if (rc || n == 0) return rc;
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
+  unsigned long long *sched = plan_sched(plan_i64, kPlanLabelTicket);
   const size_t hist_smem = ((size_t)C * C <= (size_t)kHistSmemBins) ? (size_t)C * C * sizeof(unsigned) : 0;
-  const int64_t threshold = plan_host[2];
-  if (labels8) rc = launch_edge_rows<uint8_t>(rowptr, col, n, nnz, labels8, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
-  else rc = launch_edge_rows<int32_t>(rowptr, col, n, nnz, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st, row_offset);
+  const int64_t threshold = plan_host[2], n_heavy = plan_host[0], n_chunks = plan_host[1];
+  const int64_t n_groups = ceil_div(n, 32);
+  // default: stream kernel with the per-node reductions folded in
+  const bool stream_form = labels8 != nullptr && (size_t)(C + 1) * (C + 1) <= (size_t)kHistSmemBins &&
+                           n + row_offset < (int64_t)INT32_MAX;
+  if (stream_form) {
+    const size_t smem = ((size_t)(C + 1) * (C + 1) + 2 * (size_t)(C + 1)) * sizeof(unsigned);
+    structure_stream_kernel<<<persistent_grid(ceil_div(n_groups, 8), 3), 256, smem, st>>>(
+        rowptr, col, n, labels8, C, threshold, cnt, node_sum, deg_nsl, match_nsl, row_offset, sched);
+    WDGH_LAUNCHED("structure_stream_kernel");
+  } else if (labels8) {
+    rc = launch_edge_rows<uint8_t>(rowptr, col, n, labels8, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st,
+                                   row_offset, sched);
+  } else {
+    rc = launch_edge_rows<int32_t>(rowptr, col, n, labels, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st,
+                                   row_offset, sched);
+  }
   if (rc) return rc;
-  return structure_finish(rowptr, col, n, labels, labels8, C, plan_i64, plan_host, counters, node_sum, deg_nsl,
-                          match_nsl, row_offset, st);
+  if (n_chunks > 0) {  // split rows: one warp per chunk
+    const unsigned grid = persistent_grid(ceil_div(n_chunks, 8), 8);
+    if (labels8)
+      structure_chunks_kernel<uint8_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels8, C, plan_i64, n_chunks, cnt,
+                                                                    deg_nsl, match_nsl, row_offset);
+    else
+      structure_chunks_kernel<int32_t><<<grid, 256, hist_smem, st>>>(rowptr, col, labels, C, plan_i64, n_chunks, cnt,
+                                                                    deg_nsl, match_nsl, row_offset);
+    WDGH_LAUNCHED("structure_chunks_kernel");
+  }
+  if (stream_form) {
+    if (n_heavy > 0) {
+      structure_heavy_nodes_kernel<<<persistent_grid(ceil_div(n_heavy, 256), 4), 256, 0, st>>>(
+          rowptr, labels, C, plan_i64, deg_nsl, match_nsl, cnt, node_sum, row_offset);
+      WDGH_LAUNCHED("structure_heavy_nodes_kernel");
+    }
+    return 0;
+  }
+  const size_t cls_smem = (C <= 2048) ? 2 * (size_t)C * sizeof(unsigned long long) : 0;
+  structure_nodes_kernel<<<persistent_grid(ceil_div(n, 256), 8), 256, cls_smem, st>>>(rowptr, n, labels, C, deg_nsl,
+                                                                                     match_nsl, cnt, node_sum, row_offset);
+  WDGH_LAUNCHED("structure_nodes_kernel");
+  return 0;
 }
 
 extern "C" int wdgh_structure_counts_coo(const int64_t *edge_index, int64_t num_edges, int64_t n,

@@ -13,8 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libwdgh_b200.so")
 
 NORM_NONE, NORM_RW, NORM_SYM = 0, 1, 2
 NORM_RW_SUM, NORM_SYM_RAW = 3, 4   # scale modes of wdgh_degree_scale / wdgh_scale_values only (include/wdgh_b200.h)
-PLAN_HEADER = 8
-UNIT = 1024
+PLAN_HEADER = 16
 SC_MATCH_ALL, SC_MATCH_LAB, SC_N_LAB, SC_N_SELF, SC_N_EMPTY, SC_NBINS, SC_N_NODES_NSL, SC_N_MULTI_NEG = range(8)
 SC_HEADER = 8
 
@@ -52,11 +51,10 @@ SIGNATURES = {
     "wdgh_column_segments": [_p, _p, _i64, _p, _i32, _p, _p],
     "wdgh_plan_heavy_flags": [_p, C.POINTER(_i64), _i64, _p, _p],
     "wdgh_spmm_csr_ranged": [_p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _int, _int,
-                             _int, _p, C.POINTER(_i64), _p, _i64, _p],
-    "wdgh_reduce_finalize": [_p, _i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _int, _int, _p, _i64, _p],
+                             _int, _p, _i32, _i32, _i64, _p, C.POINTER(_i64), _p, _i64, _p],
     "wdgh_structure_counts": [_p, _p, _i64, _i64, _p, _i32, _p, C.POINTER(_i64), _p, _p, _p, _p, _p, _i64, _i64, _p],
     "wdgh_spmm_structure_fused": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _i32, _p,
-                                  C.POINTER(_i64), _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p],
+                                  C.POINTER(_i64), _p, _p, _p, _p, _p, _p, _i64, _i64, _p],
     "wdgh_structure_counts_coo": [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _int, _p],
     "wdgh_edge_label_rows_equal": [_p, _p, _i64, _p, _i64, _i64, _p, _p],
     "wdgh_edge_cosine": [_p, _p, _p, _i64, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p],

@@ -109,7 +109,7 @@ class CSRGraph:
         """(device plan tensor, host int64[4] ctypes array) -- built once per graph."""
         if self._plan is None:
             cap = 2 * self.nnz // self.threshold + 2
-            words = _lib.PLAN_HEADER + 3 * cap + (self.nnz + _lib.UNIT - 1) // _lib.UNIT
+            words = _lib.PLAN_HEADER + 3 * cap
             plan = torch.empty(words, dtype=torch.int64, device=self.device)
             host = (C.c_int64 * 8)()
             check(lib.wdgh_plan_build(ptr(self.rowptr), self.n, self.nnz, self.threshold, ptr(plan), cap, host,
@@ -124,10 +124,6 @@ class CSRGraph:
     @property
     def n_heavy(self):
         return int(self.plan[1][0])
-
-    @property
-    def n_units(self):
-        return int(self.plan[1][5])
 
     def rows(self):
         """int64 row id of every stored entry (COO view)."""
@@ -222,12 +218,9 @@ def spmm(g: CSRGraph, x, norm=NORM_NONE, add_self_loop=False, out=None, dinv=Non
 
 
 def _partial_scratch(g: CSRGraph, d: int):
-    """Scratch for rows whose sum is assembled from pieces: split rows (n_chunks x d) and, only for the experimental
-    nnz-balanced stream variant (WDGH_SPMM_VARIANT=2), two partial rows per 1024-entry stream unit."""
-    import os
+    """Scratch for the rows whose sum is assembled from pieces: one partial row per chunk of a split row."""
     ldp = (d + 3) & ~3
-    units = 2 * g.n_units if os.environ.get("WDGH_SPMM_VARIANT") == "2" else 0
-    n_part = max(g.n_chunks, units) * ldp
+    n_part = g.n_chunks * ldp
     partial = g._partial.get(n_part)
     if partial is None and n_part:
         partial = torch.empty(n_part, dtype=torch.float32, device=g.device)
@@ -253,33 +246,28 @@ def heavy_flags(g: CSRGraph):
 
 
 def spmm_ranged(g: CSRGraph, range_begin, range_end, x, y, norm, add_self_loop, dinv, deg_code, skip_rows,
-                accumulate, finalize, run_split_rows, x_row0=0):
+                accumulate, finalize, run_split_rows, x_row0=0, extra=(), extra_split=0):
     """One phase of the aggregation: entries [range_begin[r], range_end[r]) of every row (see wdgh_spmm_csr_ranged).
 
     x_row0: global node id of x[0] -- lets a phase that only touches columns [x_row0, x_row0 + len(x)) read a
-    feature shard in place (the kernel is handed the address x[0] would have at global id 0)."""
+    feature shard in place (the kernel is handed the address x[0] would have at global id 0).
+    extra: raw partial sums of the same rows ([n, d] tensors, possibly peer-mapped) added as each row is stored;
+    the split-row pass adds only the last `extra_split` of them.  y may be a raw device address (peer memory)."""
     d = int(x.shape[1])
     x_ptr = x.data_ptr() - int(x_row0) * x.stride(0) * 4
     plan, plan_host = g.plan
     partial = _partial_scratch(g, d)
+    arr, ld_extra = None, 0
+    if extra:
+        ld_extra = int(extra[0].stride(0))
+        assert all(int(e.stride(0)) == ld_extra and e.shape[0] >= g.n and e.shape[1] == d for e in extra)
+        arr = C.cast((C.c_void_p * len(extra))(*[e.data_ptr() for e in extra]), C.c_void_p)
     check(lib.wdgh_spmm_csr_ranged(ptr(g.rowptr), ptr(range_begin), ptr(range_end), ptr(g.col), ptr(g.val), g.n,
                                    x_ptr, d, x.stride(0), ptr(y), y.stride(0), norm, int(bool(add_self_loop)),
                                    ptr(dinv), ptr(deg_code), ptr(skip_rows), int(bool(accumulate)), int(bool(finalize)),
-                                   int(bool(run_split_rows)), ptr(plan), plan_host, ptr(partial), g.row_offset,
-                                   stream_ptr()), "wdgh_spmm_csr_ranged")
-    return y
-
-
-def reduce_finalize(parts, x, y, norm, add_self_loop, dinv, row_offset):
-    """y[r] = s_r * (sum_p parts[p][r] + self loop) -- epilogue of the 2-D partition (see wdgh_reduce_finalize)."""
-    rows, d = int(y.shape[0]), int(y.shape[1])
-    arr = (C.c_void_p * len(parts))(*[p.data_ptr() for p in parts])
-    ld = parts[0].stride(0)
-    assert all(p.stride(0) == ld and p.shape[0] >= rows and p.shape[1] == d for p in parts)
-    check(lib.wdgh_reduce_finalize(C.cast(arr, C.c_void_p), len(parts), rows, d, ld, ptr(x),
-                                   x.stride(0) if x is not None else d, ptr(y), y.stride(0), norm,
-                                   int(bool(add_self_loop)), ptr(dinv), int(row_offset), stream_ptr()),
-          "wdgh_reduce_finalize")
+                                   int(bool(run_split_rows)), arr, len(extra), int(extra_split), ld_extra,
+                                   ptr(plan), plan_host, ptr(partial), g.row_offset, stream_ptr()),
+          "wdgh_spmm_csr_ranged")
     return y
 
 
@@ -369,10 +357,8 @@ def structure_counts(g: CSRGraph, labels32, num_classes) -> StructureCounts:
 
 
 def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, add_self_loop=True, out=None,
-                         dinv=None, deg_code=None, scratch=None, single_kernel=False):
+                         dinv=None, deg_code=None, scratch=None):
     """One call: y = norm(A [+I]) x and the label statistics (device tensors, no sync).
-
-    single_kernel=True folds the label pass into the aggregation kernel (same results, measured slower).
 
     Returns (y, (counters, node_sum, deg, match, labels_u8)); binary adjacency only."""
     if g.val is not None:
@@ -398,7 +384,7 @@ def spmm_structure_fused(g: CSRGraph, x, labels32, num_classes, norm=NORM_SYM, a
                                         y.stride(0), norm, int(bool(add_self_loop)), ptr(dinv), ptr(deg_code),
                                         ptr(labels32), c, ptr(plan), plan_host, ptr(partial), ptr(counters),
                                         ptr(node_sum), ptr(deg), ptr(match), ptr(lab8), n_labels, g.row_offset,
-                                        int(bool(single_kernel)), stream_ptr()), "wdgh_spmm_structure_fused")
+                                        stream_ptr()), "wdgh_spmm_structure_fused")
     return y, scratch
 
 
@@ -445,12 +431,12 @@ def edge_cosine(g: CSRGraph, x, entry_ids=None, raw_dot=False):
 # ---------------------------------------------------------------------------
 # dense contractions
 # ---------------------------------------------------------------------------
+GRAM_SIMT, GRAM_TC, GRAM_TC_FAITHFUL = 0, 1, 2   # include/wdgh_b200.h
 USE_TENSOR_CORES = True  # tcgen05 / TMEM Gram (csrc/gram_tc.cu); False selects the SIMT fp32 cross-check kernel
-# The KR metric feeds its Gram to np.linalg.pinv(rcond=1e-15): the matrix is rank-deficient (rank <= d),
-# so rounding noise of the Gram is amplified into the predictions.  The float32-FMA SIMT kernel reproduces
-# the reference's torch.mm noise level (golden p-values match); the 3xTF32 tensor-core result is within
-# 1e-5 of the exact Gram but not noise-compatible, so KR defaults to the SIMT kernel.
-KR_USE_TENSOR_CORES = False
+# The KR metric feeds its Gram to np.linalg.pinv(rcond=1e-15): the matrix is rank-deficient (rank <= d), so rounding
+# noise of the Gram is amplified into the predictions.  KR therefore uses the fp32-faithful tensor-core mode (every
+# k-block drained from TMEM and added in fp32 registers); False falls back to the SIMT fp32-FMA kernel.
+KR_USE_TENSOR_CORES = True
 
 
 def gather_rows(x, ids):
@@ -462,16 +448,17 @@ def gather_rows(x, ids):
     return out
 
 
-def gram(z, use_tensor_cores=None):
-    """g = z z^T (float32)."""
+def gram(z, use_tensor_cores=None, faithful=False):
+    """g = z z^T (float32).  faithful=True: fp32-level accumulation on the tensor cores (KR path)."""
     z = _cuda(z, torch.float32)
     m, d = int(z.shape[0]), int(z.shape[1])
     g = torch.empty((m, m), dtype=torch.float32, device=z.device)
     tc = USE_TENSOR_CORES if use_tensor_cores is None else use_tensor_cores
+    mode = (GRAM_TC_FAITHFUL if faithful else GRAM_TC) if tc else GRAM_SIMT
     ws = None
     if tc:
         ws = torch.empty(int(lib.wdgh_gram_workspace_floats(m, d)), dtype=torch.float32, device=z.device)
-    check(lib.wdgh_gram(ptr(z), m, d, z.stride(0), ptr(g), m, int(bool(tc)), ptr(ws), stream_ptr()), "wdgh_gram")
+    check(lib.wdgh_gram(ptr(z), m, d, z.stride(0), ptr(g), m, mode, ptr(ws), stream_ptr()), "wdgh_gram")
     return g
 
 

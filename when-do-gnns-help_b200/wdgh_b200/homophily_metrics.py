@@ -248,9 +248,9 @@ def gntk_homophily_(features, adj, sample, n_layers, _z=None):
     z = _propagate(adj, features) if _z is None else _z
     x = G._cuda(features, torch.float32)
     ids = _ids(sample, z.device)
-    tc = G.KR_USE_TENSOR_CORES  # see wdgh_b200/graph.py: pinv amplifies Gram rounding noise
-    k_g = G.gntk_transform_(G.gram(G.gather_rows(z, ids), use_tensor_cores=tc), 1 if n_layers == 1 else 0)
-    k_x = G.gntk_transform_(G.gram(G.gather_rows(x, ids), use_tensor_cores=tc), 1 if n_layers == 1 else 0)
+    tc = G.KR_USE_TENSOR_CORES  # see wdgh_b200/graph.py: pinv amplifies Gram rounding noise -> fp32-faithful mode
+    k_g = G.gntk_transform_(G.gram(G.gather_rows(z, ids), use_tensor_cores=tc, faithful=True), 1 if n_layers == 1 else 0)
+    k_x = G.gntk_transform_(G.gram(G.gather_rows(x, ids), use_tensor_cores=tc, faithful=True), 1 if n_layers == 1 else 0)
     return k_g, k_x
 
 

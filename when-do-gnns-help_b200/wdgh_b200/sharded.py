@@ -5,13 +5,14 @@ matching feature rows and labels.  Two pipelines share that ownership:
 
 * `ShardedStats` / `CudaShardedStats` -- 1-D row partition.  One step =
       all-gather(labels, degree scales)                      -- NCCL over NVLink (gloo in CPU tests)
-      features of the other ranks                            -- NCCL all-gather, or copy-engine pulls of peer-mapped
-                                                                shards with one aggregation phase per arriving shard
+      features of the other ranks                            -- copy-engine pulls of peer-mapped shards with one
+                                                                aggregation phase per arriving shard (or NCCL all-gather)
       local  A_hat[rows_r, :] X  and local label statistics  -- the same CUDA kernels as on one GPU
       all-reduce(class histograms + counters)                -- SUM (MAX for the bincount length)
-* `Grid2D` / `Cuda2DShardedStats` -- 2-D (row group x column group) partition for N >= 4: a rank aggregates the block
-  A[rows of its row group, columns of its column group], needs only its column group's feature shards and pushes
-  partial row slices to their owners (copy engines over NVLink), where `wdgh_reduce_finalize` completes them.
+* `Grid2D` / `Cuda2DShardedStats` -- 2-D (row group x column group) partition for even N: a rank aggregates the block
+  A[rows of its row group, columns of its column group], needs only its column group's feature shards, stores the
+  foreign row slices straight into their owners' memory from inside the aggregation kernel (NVLink peer stores) and
+  finishes its own slice -- reduction over the received slices, self loop, scale -- in its last aggregation phase.
 
 The aggregation output stays row-sharded in both.  Only `torch.distributed` plumbing and index arithmetic live here;
 in `ShardedStats` the local compute is injected through two methods so that the gloo tests can drive the same
@@ -126,29 +127,54 @@ class ShardedStats:
         return y_local, counters, node_sum
 
 
-class CudaShardedStats(ShardedStats):
-    """The product: local compute = the CUDA kernels of libwdgh_b200.so on this rank's GPU."""
+def _symmetric_features(x_local, rank, world, block, group):
+    """Peer-mapped feature buffer indexed by GLOBAL node id: this rank's shard lives in place at rows
+    [rank*block, (rank+1)*block), every other block is NaN until a pull fills it (an aggregation phase that reads a
+    block nobody filled shows up as NaN instead of as a plausible number).
 
-    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None, slabs=None,
-                 phased=None):
+    Returns (x_full, handle, why): handle is None when the ranks could not ALL map each other (then x_full is plain
+    memory for an NCCL all-gather); the decision is taken collectively so that every rank runs the same path."""
+    d = int(x_local.shape[1])
+    dev = x_local.device
+    ok, why, x_full, hdl = 1, "", None, None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        x_full = symm_mem.empty((world * block, d), dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(x_full, group=group if group is not None else dist.group.WORLD)
+        hdl.get_buffer((rank + 1) % world, (world * block, d), torch.float32)
+    except Exception as e:  # no peer access on this box
+        ok, why = 0, repr(e)
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        hdl = None
+        x_full = torch.empty((world * block, d), dtype=torch.float32, device=dev)
+        why = why or "a peer rank could not map the symmetric buffer"
+    x_full.fill_(float("nan"))
+    x_full[rank * block:rank * block + x_local.shape[0]].copy_(x_local)
+    if x_local.shape[0] < block:
+        x_full[rank * block + x_local.shape[0]:(rank + 1) * block].zero_()
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    return x_full, hdl, why
+
+
+class CudaShardedStats(ShardedStats):
+    """The product, 1-D row partition: local compute = the CUDA kernels of libwdgh_b200.so on this rank's GPU.
+
+    phased (default for binary graphs with a row-group width): every rank maps its peers' feature shards (symmetric
+    memory over NVLink) and pulls them with the copy engines; the aggregation runs as one `wdgh_spmm_csr_ranged`
+    phase per source rank -- local columns straight away, then one `y +=` phase per arriving shard, self loop + scale
+    in the last one.  Otherwise: NCCL all-gather of the features, then one aggregation launch."""
+
+    def __init__(self, graph_local, part, rank, x_local, labels32_local, num_classes, group=None, phased=None):
         from . import graph as G
         self._G = G
         self.g = graph_local
         d = int(x_local.shape[1])
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        if slabs is None:
-            # Column slabs of the feature matrix (gather of slab s+1 overlapping the aggregation of slab s) are
-            # supported but OFF: measured on 2 x B200, 1B-entry graph, d = 128: 1 slab 76.2 ms, 2 slabs 91.2 ms,
-            # 4 slabs 130.6 ms per step -- the gather kernel is bound by the number of random row requests, not
-            # by their size, so every extra slab costs almost a full aggregation pass.
-            slabs = 1
-        if d % slabs or (d // slabs) % 32:
-            raise ValueError("feature width must split into slabs that are multiples of 32 columns")
-        self.slabs = int(slabs)
-        # Phased aggregation: the entries whose source node is local are aggregated while the feature all-gather
-        # is in flight, the remote columns afterwards (two accumulate passes over Y).
         ok_width = (d % 4 == 0) and (d >= 128 or d in (32, 64)) and graph_local.val is None
-        self.phased = bool(ok_width and world > 1 and self.slabs == 1) if phased is None else bool(phased)
+        self.phased = bool(ok_width and world > 1) if phased is None else bool(phased)
         self._seg = None
         self._skip = None
         if graph_local.row_offset != part.bounds(rank)[0] or graph_local.n != part.rows(rank):
@@ -157,10 +183,18 @@ class CudaShardedStats(ShardedStats):
         self._scratch = None
         self._y = None
         self._x_full = None
-        # slab-major copy of the local feature rows: each slab is one contiguous all-gather payload
-        ds = d // self.slabs
-        self._x_slabs = ([self.x_local] if self.slabs == 1 else
-                         [self.x_local[:, k * ds:(k + 1) * ds].contiguous() for k in range(self.slabs)])
+        self._hdl = None
+        self._peers = None
+        self._why_no_peers = ""
+        if self.phased:
+            blk = part.block
+            self._x_full, self._hdl, self._why_no_peers = _symmetric_features(self.x_local, rank, world, blk, group)
+            self.x_local = self._x_full[rank * blk:(rank + 1) * blk]   # the shard lives in place from now on
+            if self._hdl is not None:
+                self._peers = [self._hdl.get_buffer(b, (world * blk, d), torch.float32)[b * blk:(b + 1) * blk]
+                               for b in range(world)]
+                self._copy_stream = torch.cuda.Stream()
+                self._events = [torch.cuda.Event() for _ in range(world)]
 
     def local_degree_scale(self, norm, add_self_loop):
         self.g._dinv.clear()  # recomputed every step: it is part of the timed path
@@ -177,9 +211,9 @@ class CudaShardedStats(ShardedStats):
         return y, self._scratch[0], self._scratch[1]
 
     def step(self, norm=_lib.NORM_SYM, add_self_loop=True):
-        """Same result as ShardedStats.step, with the feature all-gather (the only large transfer:
-        (N-1)/N of the feature matrix per rank over NVLink) issued asynchronously so that the label pass,
-        which needs only the gathered labels, runs underneath it."""
+        """Same result as ShardedStats.step, with the feature transfer (the only large one: (N-1)/N of the feature
+        matrix per rank over NVLink) issued asynchronously so that the label pass, which needs only the gathered
+        labels, runs underneath it."""
         G = self._G
         labels_full = _all_gather_rows(self.labels_local, self.group)
         dinv_full = None
@@ -193,20 +227,14 @@ class CudaShardedStats(ShardedStats):
         d = int(self.x_local.shape[1])
         if self.phased:
             return self._step_phased(labels_full, dinv_full, norm, add_self_loop, world, d)
-        ds = d // self.slabs
         if self._x_full is None:
-            self._x_full = [xs.new_empty((world * xs.shape[0], ds)) for xs in self._x_slabs]
-        # all slab gathers are queued back to back on the collective stream ...
-        works = [dist.all_gather_into_tensor(buf, xs, group=self.group, async_op=True)
-                 for buf, xs in zip(self._x_full, self._x_slabs)]
-        # ... the label pass and then the aggregation of slab s run while slab s+1 is still in flight
-        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)
+            self._x_full = self.x_local.new_empty((world * self.x_local.shape[0], d))
+        work = dist.all_gather_into_tensor(self._x_full, self.x_local, group=self.group, async_op=True)
+        self._scratch = G.structure_counts_raw(self.g, labels_full, self.c, self._scratch)   # under the all-gather
         if self._y is None or self._y.shape[1] != d:
             self._y = torch.empty((self.g.n, d), dtype=torch.float32, device=self.x_local.device)
-        for k, (work, buf) in enumerate(zip(works, self._x_full)):
-            work.wait()
-            G.spmm(self.g, buf, norm, add_self_loop, out=self._y[:, k * ds:(k + 1) * ds], dinv=dinv_full,
-                   deg_code=self.code_full)
+        work.wait()
+        G.spmm(self.g, self._x_full, norm, add_self_loop, out=self._y, dinv=dinv_full, deg_code=self.code_full)
         counters, node_sum = self.reduce_counters(self._scratch[0], self._scratch[1])
         return self._y, counters, node_sum
 
@@ -218,45 +246,21 @@ class CudaShardedStats(ShardedStats):
         self._seg = None
         self._skip = None
 
-    def _setup_phased(self, world, d):
-        G = self._G
-        g = self.g
-        bounds = [b * self.part.block for b in range(world)] + [max(world * self.part.block, g.n_global)]
-        self._seg = G.column_segments(g, bounds)          # per graph, like the plan
-        self._skip = G.heavy_flags(g) if g.n_chunks else None
-        if getattr(self, "_peers_ready", False):
-            return
-        self._peers_ready = True
-        self._x_full = [self.x_local.new_empty((world * self.x_local.shape[0], d))]
-        self._peers = None
-        try:  # NVLink peer mapping of every rank's shard (torch symmetric memory): pulls run on the copy engines
-            import torch.distributed._symmetric_memory as symm_mem
-            shard = symm_mem.empty(tuple(self.x_local.shape), dtype=torch.float32, device=self.x_local.device)
-            shard.copy_(self.x_local)
-            hdl = symm_mem.rendezvous(shard, group=self.group if self.group is not None else dist.group.WORLD)
-            self._shard, self._hdl = shard, hdl
-            self._peers = [hdl.get_buffer(b, tuple(self.x_local.shape), torch.float32) for b in range(world)]
-            self.x_local = shard
-            self._copy_stream = torch.cuda.Stream()
-            self._events = [torch.cuda.Event() for _ in range(world)]
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)
-        except Exception as e:  # no peer access: NCCL all-gather, local columns first, remote columns afterwards
-            self._peers = None
-            self._why_no_peers = repr(e)
-
     def _step_phased(self, labels_full, dinv_full, norm, add_self_loop, world, d):
         G = self._G
         g, r = self.g, self.rank
-        if self._seg is None:
-            self._setup_phased(world, d)
-        x_full, seg = self._x_full[0], self._seg
+        if self._seg is None:  # per graph, like the plan
+            bounds = [b * self.part.block for b in range(world)] + [max(world * self.part.block, g.n_global)]
+            self._seg = G.column_segments(g, bounds)
+            self._skip = G.heavy_flags(g) if g.n_chunks else None
+        x_full, seg = self._x_full, self._seg
         block = self.part.block
         if self._y is None or self._y.shape[1] != d:
             self._y = torch.empty((g.n, d), dtype=torch.float32, device=self.x_local.device)
         cur = torch.cuda.current_stream()
         if self._peers is not None:
-            # pulls start once everything queued so far (the previous step still reads x_full) has finished
+            # the pulls start once everything queued so far has finished: the previous step still reads x_full, and the
+            # small all-gathers above order this step after the peers' writes to their shards
             self._copy_stream.wait_stream(cur)
             order = [(r - k) % world for k in range(1, world)]
             with torch.cuda.stream(self._copy_stream):
@@ -265,17 +269,21 @@ class CudaShardedStats(ShardedStats):
                     self._events[src].record(self._copy_stream)
         else:
             work = dist.all_gather_into_tensor(x_full, self.x_local, group=self.group, async_op=True)
-        # under the transfers: label pass, then the entries whose source node is local, straight from the shard
+        # under the transfers: label pass, then the entries whose source node is local (the shard is in place)
         self._scratch = G.structure_counts_raw(g, labels_full, self.c, self._scratch)
-        G.spmm_ranged(g, seg[r], seg[r + 1], self.x_local, self._y, norm, add_self_loop, dinv_full, self.code_full,
-                      self._skip, accumulate=False, finalize=False, run_split_rows=False, x_row0=g.row_offset)
         if self._peers is not None:
+            G.spmm_ranged(g, seg[r], seg[r + 1], x_full, self._y, norm, add_self_loop, dinv_full, self.code_full,
+                          self._skip, accumulate=False, finalize=False, run_split_rows=False)
             for i, src in enumerate(order):  # one phase per shard, in arrival order
                 cur.wait_event(self._events[src])
                 last = i == len(order) - 1
                 G.spmm_ranged(g, seg[src], seg[src + 1], x_full, self._y, norm, add_self_loop, dinv_full,
                               self.code_full, self._skip, accumulate=True, finalize=last, run_split_rows=last)
         else:
+            # NCCL writes every block of x_full, the own one included: local columns from the shard meanwhile
+            G.spmm_ranged(g, seg[r], seg[r + 1], self.x_local, self._y, norm, add_self_loop, dinv_full,
+                          self.code_full, self._skip, accumulate=False, finalize=False, run_split_rows=False,
+                          x_row0=g.row_offset)
             work.wait()
             first, last = r == 0, r == world - 1
             if not first:  # columns owned by ranks 0 .. r-1
@@ -343,16 +351,28 @@ class Grid2D:
 
 
 class Cuda2DShardedStats:
-    """A_hat X on the 2-D partition + label statistics on the 1-D row shard (see Grid2D).
+    """A_hat X on the 2-D partition (2 row groups x N/2 column groups) + label statistics on the 1-D row shard.
 
-    Per step: pull the partner shards of the column group (copy engines, peer-mapped memory) while the label pass
-    runs; aggregate the pc row slices of the block one after the other (raw partial sums), PUSHING each finished
-    foreign slice into its owner's receive buffer with the copy engines while the next slice is aggregated; one
-    tiny all-reduce as barrier; `wdgh_reduce_finalize` sums own + received partials and applies self loop + scale."""
+    Rank (i, j) aggregates the block A[rows of row group i, columns of column group j]: the pc row slices of its row
+    group, restricted to the two feature shards of its column group (its own, in place, and the partner's, pulled).
+    One step:
+      1. all-gather(labels) -- also the step barrier; then the partner shard is PULLED by the copy engines;
+      2. under the pull: degree scales, label pass, and the own row slice over the columns of the OWN shard
+         (raw partial sums into receive slot 0);
+      3. the pc - 1 foreign row slices, full column range: the aggregation kernel stores every finished row straight
+         into its owner's receive slot over NVLink (peer-mapped memory) -- compute and transfer are one kernel;
+      4. a tiny all-reduce orders the peers' stores before
+      5. the own row slice over the columns of the PARTNER shard, which adds slot 0 and the pc - 1 slices received
+         from the peers as every row is stored and applies self loop + scale: the last aggregation phase IS the
+         reduction and the epilogue (no separate reduce pass, no local copy of the foreign partials);
+      6. all-reduce of the class histograms + counters.
+    Per rank 1 + (pc - 1) shards cross NVLink in each direction instead of N - 1."""
 
     def __init__(self, grid: Grid2D, rank: int, slice_graphs, graph_1d, x_local, labels32_local, num_classes, group=None):
         from . import graph as G
         import torch.distributed._symmetric_memory as symm_mem
+        if grid.pr != 2:
+            raise ValueError("the 2-D pipeline is written for 2 row groups (one partner shard per rank)")
         self._G, self.grid, self.rank, self.group = G, grid, rank, group
         self.i, self.j = grid.coords(rank)
         self.slices = slice_graphs          # pc CSRGraphs: rows of rank i*pc+s, columns of group j (global ids)
@@ -363,42 +383,33 @@ class Cuda2DShardedStats:
         dev = x_local.device
         self.labels_local = _pad_rows(labels32_local, blk)
         wgroup = group if group is not None else dist.group.WORLD
-        # symmetric (peer-mapped) buffers.  x_full is indexed by global node id; my own shard lives in place at
-        # rows [rank*blk, (rank+1)*blk) (write features through `x_shard`), the partner shards of my column group
-        # are pulled into their global positions, the rest of the buffer is never touched.
-        self.x_full = symm_mem.empty((grid.world * blk, d), dtype=torch.float32, device=dev)
+        # symmetric (peer-mapped) buffers.  x_full is indexed by global node id; my own shard lives in place (write
+        # features through `x_shard`), the partner shard is pulled into its global position, the other blocks are
+        # never touched (they stay NaN: reading one would be a bug and shows).
+        self.x_full, self._hx, why = _symmetric_features(x_local, rank, grid.world, blk, group)
+        if self._hx is None:
+            raise RuntimeError(f"the 2-D pipeline needs peer-mapped memory between all ranks: {why}")
         self.x_shard = self.x_full[rank * blk:(rank + 1) * blk]
-        self.x_shard.zero_()
-        self.x_shard[:x_local.shape[0]].copy_(x_local)
-        self._hx = symm_mem.rendezvous(self.x_full, group=wgroup)
-        self.recv = symm_mem.empty((pc, blk, d), dtype=torch.float32, device=dev)   # slot k: partial from (j-k) % pc
+        # receive slots: [0] = my own slice over my own shard's columns (local), [k] = partial of my rows from the
+        # rank k places to the left in my row group (stored by that rank's kernel over NVLink)
+        self.recv = symm_mem.empty((pc, blk, d), dtype=torch.float32, device=dev)
+        self.recv.fill_(float("nan"))
         self._hr = symm_mem.rendezvous(self.recv, group=wgroup)
-        self.partial = torch.empty((pc, blk, d), dtype=torch.float32, device=dev)   # my partial sums per row slice
-        self._peer_x = {src: self._hx.get_buffer(src, (grid.world * blk, d), torch.float32)[src * blk:(src + 1) * blk]
-                        for src in grid.col_group_ranks(self.j) if src != rank}
-        self._peer_recv = {r: self._hr.get_buffer(r, (pc, blk, d), torch.float32) for r in grid.row_group_ranks(self.i)}
+        self.partner = (1 - self.i) * pc + self.j
+        self._peer_x = self._hx.get_buffer(self.partner, (grid.world * blk, d), torch.float32)[
+            self.partner * blk:(self.partner + 1) * blk]
+        self._peer_recv = {r: self._hr.get_buffer(r, (pc, blk, d), torch.float32)
+                           for r in grid.row_group_ranks(self.i) if r != rank}
         self._copy = torch.cuda.Stream()
-        self._ev_x = torch.cuda.Event()
-        self._ev_slice = [torch.cuda.Event() for _ in range(pc)]
-        self._ev_pushed = torch.cuda.Event()
+        self._ev_ready, self._ev_x = torch.cuda.Event(), torch.cuda.Event()
         self._tiny = torch.zeros(1, dtype=torch.int32, device=dev)
         self._scratch = None
         self._y = torch.empty((self.g1d.n, d), dtype=torch.float32, device=dev)
         self._skip = [G.heavy_flags(g) if g.n_chunks else None for g in self.slices]
+        g_own = self.slices[self.j]
+        self._seg_own = G.column_segments(g_own, [rank * blk, (rank + 1) * blk])   # [lo, hi) = my shard's columns
         self.stage_ms = None            # WDGH_STAGE_TIMES=1: per-stage device times of the last step
         self._trace = os.environ.get("WDGH_STAGE_TIMES") == "1"
-        # WDGH_2D_DIRECT=1: the aggregation kernel stores foreign row slices straight into the owner's receive
-        # buffer over NVLink (no local partial buffer, no copy-engine push)
-        self._direct = os.environ.get("WDGH_2D_DIRECT", "0") == "1"
-        # WDGH_2D_SPLIT_FIRST=1: the first row slice is aggregated in two phases -- the entries whose source node lies
-        # in this rank's own shard while the partner shards are still being pulled, the rest after they arrived
-        # (`y +=`, like the 1-D phased step) -- and the pulls start right after the first small all-gather.
-        self._split_first = os.environ.get("WDGH_2D_SPLIT_FIRST", "0") == "1" and grid.pr > 1
-        self._seg_first = None
-        if self._split_first:
-            _, s1, _ = grid.schedule(rank)[0]
-            self._seg_first = G.column_segments(self.slices[s1], [rank * blk, (rank + 1) * blk])
-        self._ev_ready = torch.cuda.Event()
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
@@ -410,16 +421,20 @@ class Cuda2DShardedStats:
 
     def step(self, norm=_lib.NORM_SYM, add_self_loop=True):
         G, grid = self._G, self.grid
-        part, pc, i, j, r = grid.part, grid.pc, self.i, self.j, self.rank
+        part, pc, j, r = grid.part, grid.pc, self.j, self.rank
         blk = part.block
         cur = torch.cuda.current_stream()
         marks = [] if self._trace else None
         self._mark(marks, "start")
+        # 1. labels; every peer has now finished its previous step (its reads of the receive slots and of x_full) and
+        #    the writes of its shard, so the pull and, later, the stores into the peers' slots may start
         labels_full = _all_gather_rows(self.labels_local, self.group)
-        if self._split_first:
-            # every peer has passed its first collective of this step, i.e. finished the previous step's reads and
-            # the writes of its shard: the pulls may start now, next to the remaining small all-gathers
-            self._ev_ready.record(cur)
+        self._ev_ready.record(cur)
+        self._copy.wait_event(self._ev_ready)
+        with torch.cuda.stream(self._copy):
+            self.x_full[self.partner * blk:(self.partner + 1) * blk].copy_(self._peer_x, non_blocking=True)
+            self._ev_x.record(self._copy)
+        # 2. under the pull
         dinv_full = code_full = None
         if norm != _lib.NORM_NONE:
             self.g1d._dinv.clear()
@@ -427,61 +442,34 @@ class Cuda2DShardedStats:
             dinv_full = _all_gather_rows(_pad_rows(dinv, blk), self.group)
             code_full = _all_gather_rows(_pad_rows(code, blk), self.group) if code is not None else None
         self._mark(marks, "small all-gathers")
-        # 1. feature shards of my column group: partner shards are pulled, my own is already in place
-        if self._split_first:
-            self._copy.wait_event(self._ev_ready)
-        else:
-            self._copy.wait_stream(cur)
-        with torch.cuda.stream(self._copy):
-            for src, buf in self._peer_x.items():
-                self.x_full[src * blk:(src + 1) * blk].copy_(buf, non_blocking=True)
-            self._ev_x.record(self._copy)
-        # 2. label pass on the 1-D shard, under the pulls
         self._scratch = G.structure_counts_raw(self.g1d, labels_full, self.c, self._scratch)
         self._mark(marks, "label pass")
-        if not self._split_first:
-            cur.wait_event(self._ev_x)
-            self._mark(marks, "wait pulls")
-        # 3. row slices of my block: foreign slices first, each pushed to its owner while the next one is aggregated
-        for k, s, owner in grid.schedule(r):
+        g_own = self.slices[j]
+        lo, hi = self._seg_own[0], self._seg_own[1]
+        G.spmm_ranged(g_own, lo, hi, self.x_full, self.recv[0], norm, add_self_loop, dinv_full, code_full,
+                      self._skip[j], accumulate=False, finalize=False, run_split_rows=False)
+        self._mark(marks, "own slice, own columns")
+        cur.wait_event(self._ev_x)
+        self._mark(marks, "wait pull")
+        # 3. foreign slices: rows leave for their owner as they are finished
+        for k, s, owner in grid.schedule(r)[:-1]:
             g = self.slices[s]
-            direct = self._direct and s != j
-            out = self._peer_recv[owner][k] if direct else self.partial[s]
-            if k == 1 and self._split_first:
-                lo, hi = self._seg_first[0], self._seg_first[1]
-                # own-shard columns first (no dependence on the pulls) ...
-                G.spmm_ranged(g, lo, hi, self.x_full, out, norm, add_self_loop, dinv_full, code_full, self._skip[s],
-                              accumulate=False, finalize=False, run_split_rows=False)
-                self._mark(marks, f"slice {s} local columns")
-                cur.wait_event(self._ev_x)
-                self._mark(marks, "wait pulls")
-                # ... then the columns of the partner shards below / above it; split rows with the last phase
-                below, above = i > 0, i < grid.pr - 1
-                if below:
-                    G.spmm_ranged(g, g.rowptr[:-1], lo, self.x_full, out, norm, add_self_loop, dinv_full, code_full,
-                                  self._skip[s], accumulate=True, finalize=False, run_split_rows=not above)
-                if above:
-                    G.spmm_ranged(g, hi, g.rowptr[1:], self.x_full, out, norm, add_self_loop, dinv_full, code_full,
-                                  self._skip[s], accumulate=True, finalize=False, run_split_rows=True)
-            else:
-                G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, out, norm, add_self_loop,
-                              dinv_full, code_full, self._skip[s], accumulate=False, finalize=False,
-                              run_split_rows=True)
-            self._mark(marks, f"slice {s}")
-            if s != j and not direct:
-                self._ev_slice[s].record(cur)
-                with torch.cuda.stream(self._copy):
-                    self._copy.wait_event(self._ev_slice[s])
-                    self._peer_recv[owner][k].copy_(self.partial[s], non_blocking=True)   # slot k at the owner
-        self._ev_pushed.record(self._copy)
-        cur.wait_event(self._ev_pushed)
-        self._mark(marks, "wait pushes")
-        # 4. every rank's pushes have landed once this tiny all-reduce completes (stream-ordered after the pushes)
-        dist.all_reduce(self._tiny, group=self.group)
-        self._mark(marks, "barrier")
-        parts = [self.partial[j]] + [self.recv[k] for k in range(1, pc)]
-        G.reduce_finalize(parts, self.x_full, self._y, norm, add_self_loop, dinv_full, r * blk)
-        self._mark(marks, "reduce + finalize")
+            G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, self._peer_recv[owner][k], norm, add_self_loop,
+                          dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True)
+            self._mark(marks, f"slice {s} -> rank {owner}")
+        # 4. every rank's stores have landed once this all-reduce completes (stream-ordered after the kernels)
+        if pc > 1:
+            dist.all_reduce(self._tiny, group=self.group)
+            self._mark(marks, "barrier")
+        # 5. own slice, partner columns + slot 0 + received slices + self loop + scale
+        if self.i == 1:   # partner shard lies below mine in the column order
+            rb, re = g_own.rowptr[:-1], lo
+        else:
+            rb, re = hi, g_own.rowptr[1:]
+        G.spmm_ranged(g_own, rb, re, self.x_full, self._y, norm, add_self_loop, dinv_full, code_full, self._skip[j],
+                      accumulate=False, finalize=True, run_split_rows=True,
+                      extra=[self.recv[k] for k in range(pc)], extra_split=pc - 1)
+        self._mark(marks, "own slice, partner columns + reduce + finalize")
         counters, node_sum = ShardedStats.reduce_counters(self, self._scratch[0], self._scratch[1])
         if marks is not None:
             self._mark(marks, "counter all-reduce")
