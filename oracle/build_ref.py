@@ -10,9 +10,13 @@ install), so "building" it means taking the modules of the path, byte for byte, 
 
     /root/reference/utils/{homophily_metrics,util_funcs,homophily_plot,datasets}.py  ->  oracle/_ref/utils/
 
-oracle/_ref/ is listed in .gitignore (the reference sources never enter the history) but not in .gpurunignore, so it
-travels to the GPU box like the built .so.  Nothing is patched: the stubs for the absent third-party imports live in
-oracle/ref_shim.py, which is ours.
+It also packs the 580 `data_synthesis/{800,4000}/<h>/adj_<h>_<s>.pt` graphs the reference ships (2000 nodes, 5 classes;
+the inputs of synthetic_plot.py:60-110) into ONE compressed archive, oracle/_ref/data_synthesis.npz, so that the sweep
+runner (tools/sweep_synthesis.py) can replay the whole sweep on the GPU box.
+
+oracle/_ref/ is listed in .gitignore (the reference sources and data never enter the history) but not in
+.gpurunignore, so it travels to the GPU box like the built .so.  Nothing is patched: the stubs for the absent
+third-party imports live in oracle/ref_shim.py, which is ours.
 """
 import hashlib
 import json
@@ -23,6 +27,33 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference"
 DST = os.path.join(HERE, "_ref")
 FILES = ["utils/homophily_metrics.py", "utils/util_funcs.py", "utils/homophily_plot.py", "utils/datasets.py"]
+
+
+def pack_data_synthesis():
+    """adj_<h>_<s>.pt / label_<h>_<s>.pt -> {"<size>/<h>/<s>/edges": int16 [2, nnz], ".../labels": int8 [n]}."""
+    import glob
+    import warnings
+
+    import numpy as np
+    import torch
+
+    dst = os.path.join(DST, "data_synthesis.npz")
+    files = sorted(glob.glob(os.path.join(SRC, "data_synthesis", "*", "*", "adj_*.pt")))
+    if os.path.exists(dst) and all(os.path.getmtime(dst) >= os.path.getmtime(f) for f in files):
+        return dst
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f in files:
+            size, h = f.split(os.sep)[-3:-1]
+            s = os.path.basename(f)[:-3].split("_")[-1]
+            adj = torch.load(f, weights_only=False).coalesce()
+            lab = torch.load(f.replace("adj_", "label_"), weights_only=False).to_dense()
+            assert adj.shape[0] < 32768 and bool((adj.values() == 1).all())
+            out[f"{size}/{h}/{s}/edges"] = adj.indices().numpy().astype(np.int16)
+            out[f"{size}/{h}/{s}/labels"] = lab.argmax(1).numpy().astype(np.int8)
+    np.savez_compressed(dst, **out)
+    return dst
 
 
 def build():
@@ -36,6 +67,7 @@ def build():
         manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
     with open(os.path.join(DST, "MANIFEST.json"), "w") as f:
         json.dump({"source": SRC, "sha256": manifest}, f, indent=1)
+    pack_data_synthesis()
     return DST
 
 

@@ -463,18 +463,28 @@ def accuracy(labels, output):
     return preds.eq(labels).double().sum() / len(labels)
 
 
-def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="kernel_reg1", epochs=100):
+def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="kernel_reg1", epochs=100, trace=None,
+              gram_fn=None, z=None):
     """`classifier_based_performance_metric` p-value.  homophily_metrics.py:260-349.
 
     Kernel-regression ('kernel_reg0' / 'kernel_reg1') and Gaussian naive Bayes
     ('gnb') classifiers; consumes torch's global RNG exactly like the reference.
+
+    trace: optional list; one dict per epoch is appended (accuracies, validation ids, arg-max predictions and, for
+    the kernel classifiers, the two kernel matrices with the train / validation index sets) -- what the parity tests
+    compare instead of the p-value alone.  gram_fn: replaces `z @ z.T` (float32 torch.mm as in the reference) to
+    probe how the predictions react to the rounding of the Gram matrix.  z: the propagated features A X when the
+    caller forms them differently (homophily_plot.py:278-368 multiplies a DENSE adjacency: `plot_kr_metric`).
     """
     from scipy.stats import ttest_ind
     from sklearn.naive_bayes import GaussianNB
 
+    gram_fn = gram_fn or (lambda m: m @ m.T)
     labels = torch.as_tensor(np.asarray(labels)).flatten().long()
     x = torch.as_tensor(np.ascontiguousarray(features), dtype=torch.float32)
-    z = torch.from_numpy(spmm(row, col, val, n, features))            # recomputed per epoch upstream
+    if z is None:
+        z = torch.from_numpy(spmm(row, col, val, n, features))        # recomputed per epoch upstream
+    z = torch.as_tensor(z, dtype=torch.float32)
     g_res, x_res, diff = torch.zeros(epochs), torch.zeros(epochs), torch.zeros(epochs)
     c = int(labels.max()) + 1
     for j in range(epochs):
@@ -488,11 +498,12 @@ def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="k
         onehot = torch.eye(c)[labels][sample]
         tr, va, te = random_disassortative_splits(labels_sample, int(labels_sample.max()) + 1)   # :278
         va = va + te                                                                   # :279
+        rec = {"va": va.clone(), "tr": tr.clone(), "labels_val": labels_sample[va].clone()}
         if base_classifier in ("kernel_reg0", "kernel_reg1"):
             nl = 0 if base_classifier == "kernel_reg0" else 1
             zs, xs = z[sample], x[sample]
-            kg = _arccos_kernel(zs @ zs.T, nl) / 2
-            kx = _arccos_kernel(xs @ xs.T, nl) / 2
+            kg = _arccos_kernel(gram_fn(zs), nl) / 2
+            kx = _arccos_kernel(gram_fn(xs), nl) / 2
             preds = []
             for k in (kg, kx):
                 ktt = k[tr][:, tr]
@@ -500,19 +511,66 @@ def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="k
                 alpha = torch.tensor(np.linalg.pinv(ktt.numpy())) @ onehot[tr]        # :286-290
                 preds.append(kvt @ alpha)
             acc_g, acc_x = accuracy(labels_sample[va], preds[0]), accuracy(labels_sample[va], preds[1])
-        elif base_classifier == "gnb":
+            rec.update(kg=kg, kx=kx, onehot_tr=onehot[tr].clone(), pred_g=preds[0].max(1)[1], pred_x=preds[1].max(1)[1])
+        elif base_classifier in ("gnb", "svm_rbf", "svm_poly", "svm_linear"):
+            from sklearn import svm
             xs, zs = x[sample], z[sample]
-            cx, cg = GaussianNB(), GaussianNB()
+            make = {"gnb": lambda: GaussianNB(),
+                    "svm_rbf": lambda: svm.SVC(kernel="rbf", gamma=0.5, C=0.1),          # hm.py:317-319
+                    "svm_poly": lambda: svm.SVC(kernel="poly", degree=3, C=1),           # hm.py:320-322
+                    "svm_linear": lambda: svm.SVC(kernel="linear")}[base_classifier]    # hm.py:323-325
+            cx, cg = make(), make()
             cx.fit(xs[tr], labels_sample[tr])
             cg.fit(zs[tr], labels_sample[tr])
-            acc_x = torch.tensor(cx.predict(xs[va])).eq(labels_sample[va]).float().mean()
-            acc_g = torch.tensor(cg.predict(zs[va])).eq(labels_sample[va]).float().mean()
+            px, pg = torch.tensor(cx.predict(xs[va])), torch.tensor(cg.predict(zs[va]))
+            acc_x = px.eq(labels_sample[va]).float().mean()
+            acc_g = pg.eq(labels_sample[va]).float().mean()
+            rec.update(pred_g=pg, pred_x=px)
         else:
             raise ValueError(base_classifier)
         diff[j] = float(acc_g > acc_x)
         g_res[j], x_res[j] = acc_g, acc_x
+        rec.update(acc_g=float(acc_g), acc_x=float(acc_x))
+        if trace is not None:
+            trace.append(rec)
     _, p = ttest_ind(x_res.numpy(), g_res.numpy(), axis=0, equal_var=False, nan_policy="propagate")   # :340
     return float(p / 2) if diff.mean() <= 0.5 else float(1 - p / 2)                     # :343-347
+
+
+def plot_kr_metric(features, adj_dense, labels, sample_max, base_classifier="kernel_reg1", epochs=100, trace=None):
+    """hp.py:278-368: the synthetic_plot.py variant -- same epochs, splits, kernels and t-test as `kr_metric`; the
+    adjacency is a dense float32 matrix, so A X is a dense torch.mm (`torch.spmm(adj, features)` on dense input)."""
+    x = torch.as_tensor(np.ascontiguousarray(features), dtype=torch.float32)
+    a = torch.as_tensor(adj_dense, dtype=torch.float32)
+    n = int(a.shape[0])
+    return kr_metric(features, None, None, None, n, labels, sample_max, base_classifier, epochs, trace=trace,
+                     z=torch.mm(a, x))
+
+
+def kr_unstable_nodes(k, tr, va, onehot_tr, rel=2e-6, trials=12, seed=0):
+    """Validation nodes whose kernel-regression arg-max is decided by rounding noise.
+
+    k: kernel matrix of one epoch (K_G / 2 or K_X / 2); tr / va: boolean masks; onehot_tr: one-hot train labels.
+    The prediction is `k[va][:, tr] @ pinv(k[tr][:, tr]) @ onehot` (hm.py:286-290) with numpy's default
+    rcond = 1e-15, i.e. singular values down to 1e-15 of the largest are inverted: noise of the Gram matrix is
+    amplified by the condition number of the train block.  A node is reported unstable when its arg-max changes
+    under any of `trials` symmetric relative perturbations of size `rel` (a few float32 ulps -- what a different
+    summation order of the same float32 Gram produces).  Returns a boolean tensor over the validation nodes.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    k = k.to(torch.float32)
+
+    def predict(km):
+        ktt, kvt = km[tr][:, tr], km[va][:, tr]
+        return (kvt @ (torch.tensor(np.linalg.pinv(ktt.numpy())) @ onehot_tr)).max(1)[1]
+
+    base = predict(k)
+    unstable = torch.zeros(base.shape[0], dtype=torch.bool)
+    for _ in range(trials):
+        e = torch.randn(k.shape, generator=gen)
+        e = (e + e.T) / 2 ** 0.5
+        unstable |= predict(k * (1 + rel * e)) != base
+    return unstable
 
 
 # ---------------------------------------------------------------------------

@@ -60,3 +60,17 @@ def plot_flow_adjacency(z):
     r = 1.0 / a.sum(1)
     r[torch.isinf(r)] = 0
     return r[:, None] * a
+
+
+def linkx_graph(z):
+    """Symmetric facebook100 adjacency of a linkx_* fixture as coalesced (row, col), rebuilt from the stored triangle."""
+    up = z["in_edges_upper"].astype(np.int64)
+    row, col = np.concatenate([up[0], up[1]]), np.concatenate([up[1], up[0]])
+    order = np.lexsort((col, row))
+    return row[order], col[order]
+
+
+def l1_normalize(x):
+    """torch.nn.functional.normalize(x, p=1, dim=1) as homophily_tests.py:95 calls it (eps = 1e-12)."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    return x / x.abs().sum(1, keepdim=True).clamp_min(1e-12)

@@ -496,9 +496,26 @@ def case_linkx():
         save("linkx_" + fname.replace(" ", "_"), **out)
 
 
+# --------------------------------------------------------------------------
+# case 7: the SVM base classifiers of the KR metric (hm.py:312-333) on texas; inputs are those of ds_texas.npz
+# --------------------------------------------------------------------------
+def case_svm():
+    adj_t, features_raw, labels = uf.full_load_data_large("texas")
+    adj_t = adj_t.coalesce()
+    features_raw, labels = features_raw.float().cpu(), labels.long().cpu()
+    out = {"in_kr_seed": np.int64(404), "in_kr_sample_max": np.int64(120), "in_kr_epochs": np.int64(3)}
+    for clf in ("svm_rbf", "svm_poly", "svm_linear"):
+        seed_all(404)
+        with capture_kr_epochs(hm) as cap:
+            p, _ = hm.classifier_based_performance_metric(features_raw, adj_t, labels, 120, base_classifier=clf, epochs=3)
+        out[f"out_kr_p_{clf}"] = np.float64(p)
+        out[f"out_kr_acc_x_{clf}"], out[f"out_kr_acc_g_{clf}"] = cap.x, cap.g
+    save("svm_texas", **out)
+
+
 if __name__ == "__main__":
     cases = {"plot": case_plot_variants, "cora": case_cora, "datasets": case_datasets, "synthetic": case_synthetic,
-             "edge": case_edge_cases, "util_norm": case_util_norm, "linkx": case_linkx}
+             "edge": case_edge_cases, "util_norm": case_util_norm, "linkx": case_linkx, "svm": case_svm}
     for name in (sys.argv[1:] or list(cases)):     # no argument = regenerate everything
         cases[name]()
     os.chdir(_cwd)

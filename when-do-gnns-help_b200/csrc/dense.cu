@@ -185,6 +185,13 @@ __global__ void gntk_diag_kernel(const float *__restrict__ g, int64_t m, int64_t
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) dsq[i] = sqrtf(g[i * ldg + i]);
 }
+// The reference evaluates the arccos kernel op by op on float32 tensors (hm.py:236-244): every product, square,
+// difference and sum is rounded separately.  `sqrt(norm^2 - g^2)` cancels catastrophically wherever two rows are
+// (nearly) parallel -- the diagonal first of all -- so a fused multiply-add there changes K by up to ~3e-5 relative,
+// and the KR metric's pinv(rcond=1e-15) turns such differences into flipped predictions.  The kernel therefore
+// mirrors torch's rounding sequence with explicit round-to-nearest intrinsics (no FMA contraction), and takes acos
+// in float64 rounded once to float32 (0.5 ulp; torch's vectorised float32 acos is a 1-ulp routine that agrees
+// with the correctly rounded value on almost every input).
 __global__ void gntk_apply_kernel(float *__restrict__ g, int64_t m, int64_t ldg, const float *__restrict__ dsq,
                                   int n_layers) {
   const float eps = 1e-8f;
@@ -197,14 +204,15 @@ __global__ void gntk_apply_kernel(float *__restrict__ g, int64_t m, int64_t ldg,
     const float v = g[i * ldg + j];
     float k;
     if (n_layers == 1) {
-      float norm = dsq[i] * dsq[j];
-      norm = (norm > eps) ? norm : eps;  // NaN norm -> (NaN > eps) false, (NaN <= eps) false -> 0*NaN + 0 in torch
-      if (isnan(dsq[i] * dsq[j])) norm = CUDART_NAN_F;
-      float ac = acosf(v / norm);
-      float root = sqrtf(norm * norm - v * v);
+      const float raw = __fmul_rn(dsq[i], dsq[j]);
+      // (norm > eps) * norm + eps * (norm <= eps): NaN fails both comparisons -> 0 * NaN + eps * 0 = NaN in torch
+      float norm = (raw > eps) ? raw : eps;
+      if (isnan(raw)) norm = CUDART_NAN_F;
+      float ac = (float)acos((double)__fdiv_rn(v, norm));
+      float root = __fsqrt_rn(__fsub_rn(__fmul_rn(norm, norm), __fmul_rn(v, v)));
       if (isnan(ac)) ac = 0.f;
       if (isnan(root)) root = 0.f;
-      k = inv_pi * (v * (pi - ac) + root);
+      k = __fmul_rn(inv_pi, __fadd_rn(__fmul_rn(v, __fsub_rn(pi, ac)), root));
     } else {
       k = v;
     }

@@ -254,11 +254,14 @@ def gntk_homophily_(features, adj, sample, n_layers, _z=None):
     return k_g, k_x
 
 
-def classifier_based_performance_metric(features, adj, labels, sample_max, base_classifier='kernel_reg1', epochs=100):
+def classifier_based_performance_metric(features, adj, labels, sample_max, base_classifier='kernel_reg1', epochs=100,
+                                        _trace=None):
     """hm.py:260-349: p-value of "graph-aware beats graph-agnostic" (KR / GNB / SVM), plus elapsed seconds.
 
     A X is computed once and stays resident (the reference recomputes it every epoch);
     sampling, pinv, sklearn and the t-test follow the reference on the host with the same RNG calls.
+    `_trace` (not part of the reference signature): a list that receives one dict per epoch -- validation mask,
+    arg-max predictions and accuracies of both classifiers -- for the parity tests.
     """
     from sklearn import svm
     from sklearn.naive_bayes import GaussianNB
@@ -294,6 +297,7 @@ def classifier_based_performance_metric(features, adj, labels, sample_max, base_
                 k_vt = kk[idx_val, :][:, idx_train]
                 preds.append(k_vt @ (torch.tensor(np.linalg.pinv(k_tt.numpy())) @ label_onehot[idx_train]))
             acc_g, acc_x = accuracy(labels_sample[idx_val], preds[0]), accuracy(labels_sample[idx_val], preds[1])
+            pred_g, pred_x = preds[0].max(1)[1], preds[1].max(1)[1]
         else:
             ids = _ids(sample, z.device)
             X = G.gather_rows(x_dev, ids).cpu()
@@ -310,11 +314,15 @@ def classifier_based_performance_metric(features, adj, labels, sample_max, base_
                 raise ValueError(f"unknown base_classifier {base_classifier!r}")
             g_clf = mk().fit(X_agg[idx_train], labels_sample[idx_train])
             x_clf = mk().fit(X[idx_train], labels_sample[idx_train])
-            acc_g = torch.mean(torch.tensor(g_clf.predict(X_agg[idx_val])).eq(labels_sample[idx_val]).float())
-            acc_x = torch.mean(torch.tensor(x_clf.predict(X[idx_val])).eq(labels_sample[idx_val]).float())
+            pred_g, pred_x = torch.tensor(g_clf.predict(X_agg[idx_val])), torch.tensor(x_clf.predict(X[idx_val]))
+            acc_g = torch.mean(pred_g.eq(labels_sample[idx_val]).float())
+            acc_x = torch.mean(pred_x.eq(labels_sample[idx_val]).float())
         diff_results[j] = (acc_g > acc_x)
         G_results[j] = acc_g
         X_results[j] = acc_x
+        if _trace is not None:
+            _trace.append({"va": idx_val.clone(), "pred_g": pred_g, "pred_x": pred_x, "acc_g": float(acc_g),
+                           "acc_x": float(acc_x)})
     _, g_aware_good_p = ttest_ind(X_results.detach().cpu(), G_results.detach().cpu(), axis=0, equal_var=False,
                                   nan_policy='propagate')
     if torch.mean(diff_results) <= 0.5:

@@ -181,8 +181,9 @@ def gntk_homophily_(features, adj, sample, n_layers, _z=None):
 
 
 def classifier_based_performance_metric(features, adj, labels, sample_max, rcond=1e-15, base_classifier='kernel_reg1',
-                                        epochs=100):
-    """hp.py:278-368: like the homophily_metrics version but returns only the p-value."""
+                                        epochs=100, _trace=None):
+    """hp.py:278-368: like the homophily_metrics version but returns only the p-value.
+    `_trace` (not part of the reference signature): list receiving one dict per epoch for the parity tests."""
     from sklearn import svm
     from sklearn.naive_bayes import GaussianNB
 
@@ -214,8 +215,9 @@ def classifier_based_performance_metric(features, adj, labels, sample_max, rcond
             for kk in (K_graph, K):
                 k_tt, k_vt = kk[idx_train, :][:, idx_train], kk[idx_val, :][:, idx_train]
                 preds.append(k_vt @ (torch.tensor(np.linalg.pinv(k_tt.numpy())) @ label_onehot[idx_train]))
-            acc_g = torch.mean(preds[0].argmax(1).eq(labels_sample[idx_val]).float())
-            acc_x = torch.mean(preds[1].argmax(1).eq(labels_sample[idx_val]).float())
+            pred_g, pred_x = preds[0].argmax(1), preds[1].argmax(1)
+            acc_g = torch.mean(pred_g.eq(labels_sample[idx_val]).float())
+            acc_x = torch.mean(pred_x.eq(labels_sample[idx_val]).float())
         else:
             ids = _ids(sample, z.device)
             X, X_agg = G.gather_rows(x_dev, ids).cpu(), G.gather_rows(z, ids).cpu()
@@ -231,10 +233,14 @@ def classifier_based_performance_metric(features, adj, labels, sample_max, rcond
                 raise ValueError(f"unknown base_classifier {base_classifier!r}")
             g_clf = mk().fit(X_agg[idx_train], labels_sample[idx_train])
             x_clf = mk().fit(X[idx_train], labels_sample[idx_train])
-            acc_g = torch.mean(torch.tensor(g_clf.predict(X_agg[idx_val])).eq(labels_sample[idx_val]).float())
-            acc_x = torch.mean(torch.tensor(x_clf.predict(X[idx_val])).eq(labels_sample[idx_val]).float())
+            pred_g, pred_x = torch.tensor(g_clf.predict(X_agg[idx_val])), torch.tensor(x_clf.predict(X[idx_val]))
+            acc_g = torch.mean(pred_g.eq(labels_sample[idx_val]).float())
+            acc_x = torch.mean(pred_x.eq(labels_sample[idx_val]).float())
         diff_results[j] = (acc_g > acc_x)
         G_results[j], X_results[j] = acc_g, acc_x
+        if _trace is not None:
+            _trace.append({"va": idx_val.clone(), "pred_g": pred_g, "pred_x": pred_x, "acc_g": float(acc_g),
+                           "acc_x": float(acc_x)})
     _, g_aware_good_p = ttest_ind(X_results.detach().cpu(), G_results.detach().cpu(), axis=0, equal_var=False,
                                   nan_policy='propagate')
     if torch.mean(diff_results) <= 0.5:
