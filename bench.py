@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-phased", action="store_true", help="N>1, 1-D: plain all-gather then aggregate (no overlap)")
     ap.add_argument("--partition", default="auto", choices=["auto", "1d", "2d"],
                     help="N>1: 1-D row partition or 2-D (2 row groups x N/2 column groups); auto = 2d for even N")
+    ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
+                    help="2-D partition: aggregate the own slice next to the NVLink-bound foreign slices on a second "
+                         "stream (auto = from 4 column groups on, i.e. N >= 8)")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the element-wise check of Y against the "
                                                                "plain all-gather + one-launch aggregation")
     ap.add_argument("--workload", default="csbm", choices=["csbm", "linkx"],
@@ -286,7 +289,8 @@ def workload_config(args, nnz):
             "norm": "sym D^-1/2 (A+I) D^-1/2 on the fly",
             "partition": (f"rows/{args.gpus}" if not getattr(args, "_use_2d", False) else
                           f"2 row groups x {args.gpus // 2} column groups (peer pull of the partner shard, foreign row "
-                          "slices stored into their owners' memory by the aggregation kernel)"),
+                          "slices stored into their owners' memory by the aggregation kernel"
+                          + (", own slice overlapped on a second stream" if getattr(args, "_overlap", False) else "") + ")"),
             "l2_policy": "inputs (feature matrix >= 25 GB at full size) are far larger than the 126 MB L2"}
 
 
@@ -480,7 +484,9 @@ def main():
             return scratch[0][0], scratch[0][1]
     else:
         if use_2d:
-            pipe = Cuda2DShardedStats(grid2, rank, slice_graphs, g, x_local, labels_local, C)
+            pipe = Cuda2DShardedStats(grid2, rank, slice_graphs, g, x_local, labels_local, C,
+                                      overlap={"auto": None, "on": True, "off": False}[args.overlap])
+            args._overlap = pipe.overlap
         else:
             pipe = CudaShardedStats(g, part, rank, x_local, labels_local, C,
                                     phased=(False if args.no_phased else None))

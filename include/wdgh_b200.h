@@ -139,11 +139,15 @@ int wdgh_plan_heavy_flags(const int64_t *plan_i64, const int64_t *plan_host, int
  *   accumulate != 0 : y += (instead of y =);   finalize != 0 : apply the self loop and the row scale now
  *   (earlier phases store raw partial sums);   run_split_rows != 0 : afterwards compute the split rows over their
  *   full column range (they need all of x; finalized or raw like the call).
- *   extra_parts_host : HOST array of n_extra (<= 8) device pointers to raw partial sums of the SAME rows
- *   (float32[n][ld_extra], local row index like y), added to every row as it is stored -- the partial of an earlier
- *   column range kept in another buffer and, in the 2-D multi-GPU partition, the row slices the peers stored into
- *   this rank's memory over NVLink: the last phase of a row slice is also its reduction + epilogue.  The split-row
- *   pass adds only the LAST n_extra_split of them (an earlier phase never stores split rows).  Needs d >= 128.
+ *   extra_parts : n_extra (<= 8) raw partial sums of the SAME rows in one device buffer, part q at
+ *   extra_parts + q * extra_part_rows * ld_extra (float32[extra_part_rows][ld_extra] each, local row index like y).
+ *   They are added to every row as virtual trailing stream entries of weight 1 (fetched in the same gather batches
+ *   as the feature rows): the partial of an earlier column range kept in another buffer and, in the 2-D multi-GPU
+ *   partition, the row slices the peers stored into this rank's memory over NVLink -- the last phase of a row slice
+ *   is also its reduction + epilogue, and with range_begin == range_end the call is a pure streaming reduction.
+ *   The split-row pass adds only the LAST n_extra_split parts (an earlier phase never stores split rows).  d >= 128.
+ *   ctas_per_sm : 0 = default grid; a smaller value leaves SM capacity to a kernel running concurrently on another
+ *   stream (the NVLink-bound foreign-slice launches of the 2-D partition run next to the HBM-bound own slice).
  *   `y` (and the extra parts) may be peer-mapped memory of another GPU.
  * Needs 16-byte aligned rows and d in {32, 64} or d >= 128. */
 int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, const int64_t *range_end,
@@ -151,7 +155,8 @@ int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_begin, cons
                          const float *x, int64_t d, int64_t ldx, float *y, int64_t ldy,
                          int norm, int add_self_loop, const float *dinv, const uint8_t *deg_code,
                          const uint8_t *skip_rows, int accumulate, int finalize, int run_split_rows,
-                         const float *const *extra_parts_host, int32_t n_extra, int32_t n_extra_split, int64_t ld_extra,
+                         const float *extra_parts, int32_t n_extra, int32_t n_extra_split,
+                         int64_t extra_part_rows, int64_t ld_extra, int32_t ctas_per_sm,
                          int64_t *plan_i64, const int64_t *plan_host, float *partial,
                          int64_t row_offset, void *stream);
 

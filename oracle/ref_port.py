@@ -502,8 +502,9 @@ def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="k
         if base_classifier in ("kernel_reg0", "kernel_reg1"):
             nl = 0 if base_classifier == "kernel_reg0" else 1
             zs, xs = z[sample], x[sample]
-            kg = _arccos_kernel(gram_fn(zs), nl) / 2
-            kx = _arccos_kernel(gram_fn(xs), nl) / 2
+            gram_g, gram_x = gram_fn(zs), gram_fn(xs)
+            kg = _arccos_kernel(gram_g, nl) / 2
+            kx = _arccos_kernel(gram_x, nl) / 2
             preds = []
             for k in (kg, kx):
                 ktt = k[tr][:, tr]
@@ -511,7 +512,8 @@ def kr_metric(features, row, col, val, n, labels, sample_max, base_classifier="k
                 alpha = torch.tensor(np.linalg.pinv(ktt.numpy())) @ onehot[tr]        # :286-290
                 preds.append(kvt @ alpha)
             acc_g, acc_x = accuracy(labels_sample[va], preds[0]), accuracy(labels_sample[va], preds[1])
-            rec.update(kg=kg, kx=kx, onehot_tr=onehot[tr].clone(), pred_g=preds[0].max(1)[1], pred_x=preds[1].max(1)[1])
+            rec.update(kg=kg, kx=kx, gram_g=gram_g, gram_x=gram_x, n_layers=nl, onehot_tr=onehot[tr].clone(),
+                       pred_g=preds[0].max(1)[1], pred_x=preds[1].max(1)[1])
         elif base_classifier in ("gnb", "svm_rbf", "svm_poly", "svm_linear"):
             from sklearn import svm
             xs, zs = x[sample], z[sample]
@@ -547,29 +549,35 @@ def plot_kr_metric(features, adj_dense, labels, sample_max, base_classifier="ker
                      z=torch.mm(a, x))
 
 
-def kr_unstable_nodes(k, tr, va, onehot_tr, rel=2e-6, trials=12, seed=0):
+def kr_unstable_nodes(gram, n_layers, tr, va, onehot_tr, rel=3e-7, trials=12, seed=0):
     """Validation nodes whose kernel-regression arg-max is decided by rounding noise.
 
-    k: kernel matrix of one epoch (K_G / 2 or K_X / 2); tr / va: boolean masks; onehot_tr: one-hot train labels.
-    The prediction is `k[va][:, tr] @ pinv(k[tr][:, tr]) @ onehot` (hm.py:286-290) with numpy's default
-    rcond = 1e-15, i.e. singular values down to 1e-15 of the largest are inverted: noise of the Gram matrix is
-    amplified by the condition number of the train block.  A node is reported unstable when its arg-max changes
-    under any of `trials` symmetric relative perturbations of size `rel` (a few float32 ulps -- what a different
-    summation order of the same float32 Gram produces).  Returns a boolean tensor over the validation nodes.
+    gram: the float32 Gram matrix of one epoch (Z Z^T of the sampled rows, before the arccos transform); tr / va:
+    boolean masks; onehot_tr: one-hot train labels.  The prediction is
+    `k[va][:, tr] @ pinv(k[tr][:, tr]) @ onehot` with k = arccos_kernel(gram) / 2 (hm.py:236-257, 286-290) and numpy's
+    default rcond = 1e-15, i.e. singular values down to 1e-15 of the largest are inverted: rounding noise of the Gram
+    matrix passes through `sqrt(norm^2 - g^2)` (which cancels wherever two rows are nearly parallel) and is then
+    amplified by the condition number of the train block.  A node is reported unstable when its arg-max changes under
+    any of `trials` symmetric perturbations G_ij += rel * sqrt(G_ii G_jj) * N(0, 1) -- the size of the float32
+    dot-product error bound (a few ulps of |z_i| |z_j|), which is what a different summation order or a different
+    float32 GEMM produces.  Returns a boolean tensor over the validation nodes.
     """
     gen = torch.Generator().manual_seed(seed)
-    k = k.to(torch.float32)
+    gram = gram.to(torch.float32)
+    d = torch.sqrt(torch.diag(gram).clamp(min=0))
+    scale = d.reshape(-1, 1) * d.reshape(1, -1)
 
-    def predict(km):
+    def predict(gm):
+        km = _arccos_kernel(gm, n_layers) / 2
         ktt, kvt = km[tr][:, tr], km[va][:, tr]
         return (kvt @ (torch.tensor(np.linalg.pinv(ktt.numpy())) @ onehot_tr)).max(1)[1]
 
-    base = predict(k)
+    base = predict(gram)
     unstable = torch.zeros(base.shape[0], dtype=torch.bool)
     for _ in range(trials):
-        e = torch.randn(k.shape, generator=gen)
+        e = torch.randn(gram.shape, generator=gen)
         e = (e + e.T) / 2 ** 0.5
-        unstable |= predict(k * (1 + rel * e)) != base
+        unstable |= predict(gram + rel * scale * e) != base
     return unstable
 
 

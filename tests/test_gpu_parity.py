@@ -136,7 +136,7 @@ def check_kr(W, z, A, x, labels, tag=""):
     reference's own p-value moving when only its float32 acos / sqrt are re-rounded), so the contract is:
       * same RNG draws: identical validation sets in every epoch;
       * every prediction OUTSIDE the set the oracle flags as noise-decided (`kr_unstable_nodes`: arg-max changes
-        under 2e-6 relative perturbations of K) equals the reference's prediction;
+        under float32-rounding-sized perturbations of the Gram matrix) equals the reference's prediction;
       * at most max(1, 5%) of an epoch's validation nodes differ at all, unless the oracle flags the whole epoch
         (>= 90% of its nodes) as noise-decided;
       * when nothing differs, the p-value matches the reference to 1e-6 and the per-epoch accuracies exactly."""
@@ -168,19 +168,20 @@ def kr_contract(clf, p, trace, ref_trace, gold_p, gold_acc_g, gold_acc_x):
     for e, (got, ref) in enumerate(zip(trace, ref_trace)):
         assert torch.equal(got["va"].cpu(), ref["va"]), (clf, e)
         n_val = int(ref["va"].sum())
-        for side, kname in (("pred_g", "kg"), ("pred_x", "kx")):
+        for side, kname in (("pred_g", "gram_g"), ("pred_x", "gram_x")):
             changed = got[side].cpu() != ref[side]
             n_diff += int(changed.sum())
             if clf == "gnb":
                 assert int(changed.sum()) <= 1, (clf, e, side)
                 continue
-            unstable = O.kr_unstable_nodes(ref[kname], ref["tr"], ref["va"], ref["onehot_tr"])
+            unstable = O.kr_unstable_nodes(ref[kname], ref["n_layers"], ref["tr"], ref["va"], ref["onehot_tr"])
             assert not bool((changed & ~unstable).any()), (clf, e, side, int(changed.sum()), int(unstable.sum()))
             # a well-conditioned epoch flips at most a few near-ties; an epoch the oracle flags as noise-decided as a
             # whole (rank-deficient train Gram under pinv(rcond=1e-15): >= 90% of the nodes unstable) is unconstrained
             assert int(changed.sum()) <= max(1, n_val // 20) or int(unstable.sum()) * 10 >= 9 * n_val, \
                 (clf, e, side, int(changed.sum()), int(unstable.sum()), n_val)
-    assert np.isfinite(float(p)) and 0.0 <= float(p) <= 1.0
+    # Welch's t-test yields NaN when both accuracy vectors are constant (zero variance) -- upstream does the same
+    assert np.isnan(float(p)) or 0.0 <= float(p) <= 1.0
     if n_diff == 0:
         close(p, gold_p, rtol=1e-6, atol=1e-12)
         np.testing.assert_allclose([t["acc_g"] for t in trace], gold_acc_g, rtol=0, atol=1e-7)
@@ -660,7 +661,7 @@ def test_2d_partition_replay_on_one_gpu(W, d, world, n):
     for owner in range(world):
         r0, r1 = grid.part.bounds(owner)
         i, s = grid.coords(owner)
-        slots = [None] * pc
+        slots = torch.full((pc, blk, d), float("nan"), device="cuda")   # the owner's receive slots, one buffer
         own = None
         for j in range(pc):     # producer rank (i, j): rows of `owner`, columns of column group j
             prod = i * pc + j
@@ -681,22 +682,29 @@ def test_2d_partition_replay_on_one_gpu(W, d, world, n):
             if prod != owner:
                 k = (s - j) % pc
                 assert grid.slot_source(owner, k) == prod and (k, s, owner) in grid.schedule(prod)
-                part = torch.full((blk, d), float("nan"), device="cuda")
-                W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_cols, part, W.NORM_SYM, True, dinv_pad, dcode,
-                                    skip, False, False, True)
-                slots[k] = part
+                # a reduced grid, as when the launch shares the SMs with the owner-side phase
+                W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[1:], x_cols, slots[k], W.NORM_SYM, True, dinv_pad, dcode,
+                                    skip, False, False, True, ctas_per_sm=16 if owner % 2 else 0)
             else:
                 own = (sg, skip, dcode, x_cols)
         sg, skip, dcode, x_cols = own
         seg = W.graph.column_segments(sg, [owner * blk, (owner + 1) * blk])
-        slots[0] = torch.full((blk, d), float("nan"), device="cuda")
         W.graph.spmm_ranged(sg, seg[0], seg[1], x_cols, slots[0], W.NORM_SYM, True, dinv_pad, dcode, skip,
                             False, False, False)
         rb, re = (sg.rowptr[:-1], seg[0]) if i == 1 else (seg[1], sg.rowptr[1:])
+        # (a) the last launch aggregates the partner columns AND reduces the slots
         y = torch.full((r1 - r0, d), float("nan"), device="cuda")
         W.graph.spmm_ranged(sg, rb, re, x_cols, y, W.NORM_SYM, True, dinv_pad, dcode, skip, False, True, True,
                             extra=slots, extra_split=pc - 1)
         err = (y - y_ref[r0:r1]).abs().max().item()
+        assert err <= 1e-5 * y_ref.abs().max().item(), (owner, err)
+        # (b) overlapped form: partner columns accumulate into slot 0, then a pure streaming reduction (empty ranges)
+        W.graph.spmm_ranged(sg, rb, re, x_cols, slots[0], W.NORM_SYM, True, dinv_pad, dcode, skip, True, False, False,
+                            ctas_per_sm=16)
+        y2 = torch.full((r1 - r0, d), float("nan"), device="cuda")
+        W.graph.spmm_ranged(sg, sg.rowptr[:-1], sg.rowptr[:-1], x_cols, y2, W.NORM_SYM, True, dinv_pad, dcode, skip,
+                            False, True, True, extra=slots, extra_split=pc - 1)
+        err = (y2 - y_ref[r0:r1]).abs().max().item()
         assert err <= 1e-5 * y_ref.abs().max().item(), (owner, err)
     assert n_heavy > 0
 

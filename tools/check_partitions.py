@@ -9,6 +9,8 @@ Every rank builds its row shard of the bench generator's graph and runs, in this
     1d-phased  peer-mapped shards pulled by the copy engines, one `y +=` phase per arriving shard
     2d         2 row groups x N/2 column groups: partner shard pulled, foreign row slices stored into their owners'
                memory by the aggregation kernel, own slice finished by its last phase (reduce + self loop + scale)
+    2d-overlap (N >= 4) the same with the own slice's partner columns aggregated NEXT TO the foreign slices on a
+               second stream and a pure streaming reduction as last launch (the default from N = 8 on)
     1d-plain   NCCL all-gather of the features, then ONE aggregation launch (the N = 1 kernel on a row shard)
 
 and compares each result (Y rows of the rank, all-reduced counters, node sum) with 1d-plain, which runs LAST so that
@@ -52,7 +54,10 @@ def check(args, n, world, rank, device, bench, W, G, CudaShardedStats, Cuda2DSha
     if world % 2 == 0:
         grid2 = Grid2D(n, world, 2)
         slices = bench.make_slice_graphs(G, grid2, rank, rowptr, col, args, device)
-        results["2d"] = run(Cuda2DShardedStats(grid2, rank, slices, g, x_local, labels_local, C))
+        results["2d"] = run(Cuda2DShardedStats(grid2, rank, slices, g, x_local, labels_local, C, overlap=False))
+        torch.cuda.empty_cache()
+        if world >= 4:   # own slice aggregated next to the foreign slices on a second stream + streaming reduction
+            results["2d-overlap"] = run(Cuda2DShardedStats(grid2, rank, slices, g, x_local, labels_local, C, overlap=True))
         del slices
         torch.cuda.empty_cache()
     results["1d-plain"] = run(CudaShardedStats(g, part, rank, x_local, labels_local, C, phased=False))

@@ -54,7 +54,9 @@ def features_for(key, labels, d=32):
     g = torch.Generator().manual_seed(int.from_bytes(key.encode(), "little") % (2 ** 31 - 1))
     c = int(labels.max()) + 1
     centers = torch.randn(c, d, generator=g)
-    return (centers[torch.from_numpy(labels)] + 1.5 * torch.randn(labels.shape[0], d, generator=g)).float()
+    # non-negative like the bag-of-words features of the reference's base datasets: `preprocess_features` divides by
+    # the row SUM, which for signed noise can be ~0 and blows single rows up by 1e3
+    return (centers[torch.from_numpy(labels)] + 1.5 * torch.randn(labels.shape[0], d, generator=g)).abs().float()
 
 
 def main():
@@ -123,7 +125,8 @@ def main():
                "class_homo": float(O.plot_class_homophily(row, col, val, labels, n)),
                "soft_las": float(O.plot_similarity(oh, row, col, val, n, oh)),
                "adj_homo": float((eh - s2) / (1 - s2)), "label_info": float(O.label_informativeness(row, col, labels, n)),
-               "gen_edge_homo": float(O.generalized_edge_homophily(row, col, x, n))}
+               # hp.py:56-65 takes the all-entries branch whenever nnodes < 20000, whatever the entry count
+               "gen_edge_homo": float(O.generalized_edge_homophily(row, col, x, n, sample_max=1 << 62))}
         ref_traces = {}
         for clf in ("kernel_reg0", "kernel_reg1"):
             seed_all(1000 + n_graphs)
@@ -132,7 +135,8 @@ def main():
         t_cpu += time.perf_counter() - t0
         # ---------------- compare (not timed) ----------------
         for k, tol in TOL.items():
-            dev = abs(got[k] - ref[k]) / (1.0 if k == "soft_las" else max(abs(ref[k]), 1e-3))
+            # label informativeness is 2 - ratio with the ratio near 2 at low h: absolute, like the golden tests (1e-5)
+            dev = abs(got[k] - ref[k]) / (1.0 if k == "soft_las" else 0.1 if k == "label_info" else max(abs(ref[k]), 1e-3))
             worst[k] = max(worst[k], dev)
             if not dev <= tol:
                 bad.append((key, k, got[k], ref[k]))
@@ -143,11 +147,11 @@ def main():
                     continue
                 kr["epochs_compared"] += 1
                 same = True
-                for side, kname in (("pred_g", "kg"), ("pred_x", "kx")):
+                for side, kname in (("pred_g", "gram_g"), ("pred_x", "gram_x")):
                     changed = g_[side].cpu() != r_[side]
                     if bool(changed.any()):
                         same = False
-                        unstable = O.kr_unstable_nodes(r_[kname], r_["tr"], r_["va"], r_["onehot_tr"])
+                        unstable = O.kr_unstable_nodes(r_[kname], r_["n_layers"], r_["tr"], r_["va"], r_["onehot_tr"])
                         kr["flips"] += int(changed.sum())
                         outside = int((changed & ~unstable).sum())
                         kr["flips_outside_unstable"] += outside

@@ -162,7 +162,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
       WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[k], 0));
       const int last = (k == K - 1);
       rc = wdgh_spmm_csr_ranged(c.rowptr, c.seg + (size_t)k * n, c.seg + (size_t)(k + 1) * n, c.col, nullptr, n, c.x, d,
-                                d, c.y, d, norm, add_self_loop, dinv, code, c.skip, k > 0, last, last, nullptr, 0, 0, 0,
+                                d, c.y, d, norm, add_self_loop, dinv, code, c.skip, k > 0, last, last, nullptr, 0, 0, 0, 0, 0,
                                 c.plan, plan_host, c.partial, 0, st);
       if (rc) return rc;
     }

@@ -202,14 +202,20 @@ spmm_chunks_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
 // Ranged / phased aggregation: the kernel normally walks CSR rows [rowptr[r], rowptr[r+1]); with row_end set it
 // walks [rowptr[r], row_end[r]) instead (a column range of every row, e.g. the entries whose source node lives on
 // one rank), optionally adding to what Y already holds and deferring the self-loop + D^-1/2 scaling to the last phase.
-// ExtraParts lists further raw partial sums of the same rows (local-row indexed like y) that are added when a row is
-// stored: the 2-D partition finishes a row slice in the launch that aggregates its last column range -- the partial
-// of the earlier range and the slices the peers stored into this rank's memory ride along, no separate reduce pass.
+// ExtraParts lists further raw partial sums of the same rows (local-row indexed like y): `n` parts of one buffer,
+// part q starting `part_rows` rows after part q - 1 (the receive slots of the 2-D partition are one [pc][rows][d]
+// array).  They enter the row's stream as VIRTUAL trailing entries with weight 1 -- like the self loop -- so they are
+// fetched in the same unpredicated gather batches as the feature rows, fully pipelined: the 2-D partition finishes a
+// row slice in the launch that aggregates its last column range (or, with an empty range, in a pure streaming
+// reduction) -- the partial of the earlier range and the slices the peers stored into this rank's memory ride along,
+// no separate reduce pass.  (Adding them when a row is flushed was measured at 4.5 TB/s: every flush stalled on a
+// dependent load; as stream entries the phase runs like any other gather pass.)
 constexpr int kMaxExtra = 8;
 struct ExtraParts {
-  int n;       // number of valid pointers
-  int64_t ld;  // row stride in floats
-  const float *p[kMaxExtra];
+  int n;                // number of parts
+  int64_t ld;           // row stride in floats
+  int64_t part_rows;    // rows between consecutive parts
+  const float *base;    // part 0, row 0
 };
 struct RangeArgs {
   const int64_t *row_end;  // nullptr: plain CSR
@@ -238,9 +244,7 @@ spmm_heavy_finish_kernel(const int64_t *__restrict__ rowptr, const float *__rest
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float acc = 0.f;
     for (int64_t p = 0; p < nch; ++p) acc += partial[(c0 + p) * ldp + c];
-#pragma unroll
-    for (int q = 0; q < kMaxExtra; ++q)
-      if (q < ex.n) acc += ex.p[q][row * ex.ld + c];
+    for (int q = 0; q < ex.n; ++q) acc += ex.base[(q * ex.part_rows + row) * ex.ld + c];
     if (self_loop && finalize) acc = fmaf(self_w, __ldg(x + grow * ldx + c), acc);
     y[row * ldy + c] = acc * si;  // finalize == 0: the raw partial sum (2-D partition: reduced across ranks later)
   }
@@ -279,6 +283,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
   const bool sym = (norm == WDGH_NORM_SYM);
   const bool coded = sym && deg_code != nullptr;
   const bool virt = self_loop && ra.finalize;  // self loop = virtual trailing entry of its row
+  const int n_virt = (virt ? 1 : 0) + (EXTRA ? ra.ex.n : 0);   // ... followed by the extra partial sums of the row
   if (coded) {
     for (int c = lane; c < 256; c += 32) {
       double rs = (double)c + (self_loop ? 1.0 : 0.0);
@@ -312,7 +317,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
     const int64_t r = (g << 5) + lane;
     const bool inr = r < n;
     const bool hv = inr && (flag != 0 || e - b > threshold);
-    int inc = (!inr || hv) ? 0 : (int)(e - b) + (virt ? 1 : 0);
+    int inc = (!inr || hv) ? 0 : (int)(e - b) + n_virt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(kFull, inc, o);
@@ -339,10 +344,18 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         if (s_off[buf][lo + step] <= t) lo += step;
       rho = lo;
       const int k = t - s_off[buf][lo];
-      if (virt && k == s_off[buf][lo + 1] - s_off[buf][lo] - 1) {
-        const int64_t grow = (g << 5) + lo + row_offset;
-        j = (int)grow;
-        w = sym ? __ldg(dinv + grow) : 1.f;
+      const int real = s_off[buf][lo + 1] - s_off[buf][lo] - n_virt;   // stored entries of this row in the stream
+      if (k >= real) {
+        const int q = k - real;
+        if (virt && q == 0) {   // the self loop
+          const int64_t grow = (g << 5) + lo + row_offset;
+          j = (int)grow;
+          w = sym ? __ldg(dinv + grow) : 1.f;
+        } else {                // part q' of the extra partial sums: row index inside the parts buffer, top bit set
+          const int64_t part = q - (virt ? 1 : 0);
+          j = (int)(0x80000000u | (unsigned)(part * ra.ex.part_rows + (g << 5) + lo));
+          w = 1.f;
+        }
       } else {
         const int64_t idx = s_beg[buf][lo] + k;
         j = __ldg(col + idx);
@@ -355,6 +368,13 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         }
       }
     }
+  };
+  // address of the feature (or extra partial) row a stream entry gathers
+  const float *el = EXTRA ? ra.ex.base + cbase + lane * VEC : nullptr;
+  const int lde32 = EXTRA ? (int)ra.ex.ld : 0;
+  auto row_ptr = [&](int ju) -> const float * {
+    if (EXTRA && ju < 0) return el + (int64_t)(ju & 0x7fffffff) * lde32;
+    return xl + (int64_t)ju * ld32;
   };
 
   // group order: a ticket counter (FULL: one column tile) -- row lengths are heavy-tailed, with tickets a warp
@@ -390,7 +410,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
       const int64_t row = (g << 5) + cur;
       const float si = __shfl_sync(kFull, si_l, cur);
       const bool had = s_off[buf][cur + 1] != s_off[buf][cur];
-      if (had || ra.finalize || !ra.accumulate || EXTRA) {  // an empty range adds nothing to an earlier phase's sum
+      if (had || ra.finalize || !ra.accumulate) {  // an empty range adds nothing to an earlier phase's sum
 #pragma unroll
         for (int t = 0; t < NCH; ++t) {
           if (live[t]) {
@@ -399,16 +419,6 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
               Vec<VEC> prev;
               prev.load_plain(y + row * ldy + c);
               acc[t].add(prev);
-            }
-            if (EXTRA) {  // partial sums of the same row from earlier phases / from the peers
-#pragma unroll
-              for (int q = 0; q < kMaxExtra; ++q) {
-                if (q < ra.ex.n) {
-                  Vec<VEC> part;
-                  part.load(ra.ex.p[q] + row * ra.ex.ld + c);
-                  acc[t].add(part);
-                }
-              }
             }
             if (ra.finalize) {
               acc[t].scale(si);
@@ -447,7 +457,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         Vec<VEC> v[U][NCH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, k + u) * ld32;
+          const float *xr = row_ptr(__shfl_sync(kFull, j, k + u));
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
             if (live[t]) v[u][t].load(xr + t * (32 * VEC));
@@ -472,7 +482,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool on = k + u < cnt;
-          const float *xr = xl + (int64_t)__shfl_sync(kFull, j, on ? k + u : 0) * ld32;
+          const float *xr = row_ptr(__shfl_sync(kFull, j, on ? k + u : 0));
 #pragma unroll
           for (int t = 0; t < NCH; ++t) {
             if (on && live[t]) v[u][t].load(xr + t * (32 * VEC));
@@ -525,7 +535,8 @@ struct SpmmArgs {
   const uint8_t *deg_code;
   int64_t *plan;
   int64_t threshold, n_heavy, n_chunks, row_offset;
-  RangeArgs ra = {nullptr, nullptr, 0, 1, {0, 0, {nullptr}}};
+  RangeArgs ra = {nullptr, nullptr, 0, 1, {0, 0, 0, nullptr}};
+  int cta_limit = 0;       // row-group kernel: CTAs per SM (0 = the default for the tile shape)
   bool heavy_pass = true;  // run the split-row chunk kernels
   float *partial;
   int64_t ldp;
@@ -570,7 +581,8 @@ static int launch_rowgroup(const SpmmArgs &a) {
   constexpr int TILE = 32 * VEC * NCH;
   constexpr int MINB = (NCH == 1) ? 32 : 16;
   const int64_t n_groups = (a.n + 31) / 32;
-  int64_t ctas = (int64_t)sm_count() * MINB;
+  const int per_sm = (a.cta_limit > 0 && a.cta_limit < MINB) ? a.cta_limit : MINB;
+  int64_t ctas = (int64_t)sm_count() * per_sm;
   if (ctas > n_groups) ctas = n_groups;
   dim3 grid((unsigned)ctas, (unsigned)ceil_div(a.d, TILE));
   const bool full = (a.d == TILE);
@@ -599,7 +611,7 @@ template <bool HAS_VAL>
 static int dispatch(const SpmmArgs &a, bool vec4) {
   int rc;
   const int d = a.d;
-  const ExtraParts none = {0, 0, {nullptr}};
+  const ExtraParts none = {0, 0, 0, nullptr};
   if (vec4 && rowgroup_width(d)) {
     if (d == 32) rc = launch_rowgroup<1, 1, HAS_VAL>(a);
     else if (d == 64) rc = launch_rowgroup<2, 1, HAS_VAL>(a);
@@ -749,9 +761,9 @@ extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_
                                     int64_t ldx, float *y, int64_t ldy, int norm, int add_self_loop,
                                     const float *dinv, const uint8_t *deg_code, const uint8_t *skip_rows,
                                     int accumulate, int finalize, int run_split_rows,
-                                    const float *const *extra_parts_host, int32_t n_extra, int32_t n_extra_split,
-                                    int64_t ld_extra, int64_t *plan_i64, const int64_t *plan_host, float *partial,
-                                    int64_t row_offset, void *stream) {
+                                    const float *extra_parts, int32_t n_extra, int32_t n_extra_split,
+                                    int64_t extra_part_rows, int64_t ld_extra, int32_t ctas_per_sm, int64_t *plan_i64,
+                                    const int64_t *plan_host, float *partial, int64_t row_offset, void *stream) {
   WDGH_REQUIRE(rowptr && range_begin && range_end && x && y && plan_i64 && plan_host, "wdgh_spmm_csr_ranged: null pointer");
   WDGH_REQUIRE(n >= 0 && d > 0 && ldx >= d && ldy >= d, "wdgh_spmm_csr_ranged: bad shape");
   WDGH_REQUIRE(norm == WDGH_NORM_NONE || dinv != nullptr, "wdgh_spmm_csr_ranged: norm requires dinv");
@@ -759,8 +771,11 @@ extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_
                "wdgh_spmm_csr_ranged: needs 16-byte aligned rows and d in {32, 64} or d >= 128");
   WDGH_REQUIRE(plan_host[1] == 0 || skip_rows != nullptr, "wdgh_spmm_csr_ranged: split rows need skip_rows (wdgh_plan_heavy_flags)");
   WDGH_REQUIRE(n_extra >= 0 && n_extra <= kMaxExtra && n_extra_split >= 0 && n_extra_split <= n_extra &&
-                   (n_extra == 0 || (extra_parts_host != nullptr && ld_extra >= d && ld_extra % 4 == 0 && d >= 128)),
+                   (n_extra == 0 || (extra_parts != nullptr && ld_extra >= d && ld_extra % 4 == 0 && d >= 128 &&
+                                     extra_part_rows >= n && reinterpret_cast<uintptr_t>(extra_parts) % 16 == 0 &&
+                                     (int64_t)n_extra * extra_part_rows < ((int64_t)1 << 31))),
                "wdgh_spmm_csr_ranged: bad extra partial sums");
+  WDGH_REQUIRE(ctas_per_sm >= 0, "wdgh_spmm_csr_ranged: bad ctas_per_sm");
   if (n == 0) return 0;
   SpmmArgs a;
   a.rowptr = range_begin; a.col = col; a.val = val; a.n = n; a.x = x; a.d = (int)d; a.ldx = ldx; a.y = y; a.ldy = ldy;
@@ -771,22 +786,18 @@ extern "C" int wdgh_spmm_csr_ranged(const int64_t *rowptr, const int64_t *range_
   a.row_offset = row_offset;
   a.st = as_stream(stream);
   a.ra.row_end = range_end; a.ra.skip = skip_rows; a.ra.accumulate = accumulate ? 1 : 0; a.ra.finalize = finalize ? 1 : 0;
-  a.ra.ex.n = n_extra; a.ra.ex.ld = ld_extra;
-  for (int q = 0; q < kMaxExtra; ++q) {
-    a.ra.ex.p[q] = q < n_extra ? extra_parts_host[q] : nullptr;
-    WDGH_REQUIRE(q >= n_extra || (a.ra.ex.p[q] != nullptr && reinterpret_cast<uintptr_t>(a.ra.ex.p[q]) % 16 == 0),
-                 "wdgh_spmm_csr_ranged: extra partial sums must be 16-byte aligned");
-  }
+  a.ra.ex = ExtraParts{n_extra, ld_extra, extra_part_rows, extra_parts};
+  a.cta_limit = ctas_per_sm;
   a.heavy_pass = false;
   int rc = val ? dispatch<true>(a, true) : dispatch<false>(a, true);
   if (rc || !run_split_rows || a.n_chunks == 0) return rc;
   // split rows: always over their full column range, after the last phase (they overwrite their Y rows); of the
   // extra partial sums only the LAST n_extra_split apply (an earlier phase of this rank never stored split rows)
   WDGH_REQUIRE(partial != nullptr, "wdgh_spmm_csr_ranged: split rows need the partial buffer");
-  ExtraParts ex = {n_extra_split, ld_extra, {nullptr}};
-  for (int q = 0; q < n_extra_split; ++q) ex.p[q] = a.ra.ex.p[n_extra - n_extra_split + q];
+  ExtraParts ex = {n_extra_split, ld_extra, extra_part_rows,
+                   n_extra ? extra_parts + (int64_t)(n_extra - n_extra_split) * extra_part_rows * ld_extra : nullptr};
   a.rowptr = rowptr; a.threshold = plan_host[2];
-  a.ra = RangeArgs{nullptr, nullptr, 0, finalize ? 1 : 0, {0, 0, {nullptr}}};
+  a.ra = RangeArgs{nullptr, nullptr, 0, finalize ? 1 : 0, {0, 0, 0, nullptr}};
   if (val) {
     if (d <= 128) return launch_heavy<4, 1, true>(a, ex);
     if (d <= 256) return launch_heavy<4, 2, true>(a, ex);

@@ -51,7 +51,7 @@ SIGNATURES = {
     "wdgh_column_segments": [_p, _p, _i64, _p, _i32, _p, _p],
     "wdgh_plan_heavy_flags": [_p, C.POINTER(_i64), _i64, _p, _p],
     "wdgh_spmm_csr_ranged": [_p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _int, _int,
-                             _int, _p, _i32, _i32, _i64, _p, C.POINTER(_i64), _p, _i64, _p],
+                             _int, _p, _i32, _i32, _i64, _i64, _i32, _p, C.POINTER(_i64), _p, _i64, _p],
     "wdgh_structure_counts": [_p, _p, _i64, _i64, _p, _i32, _p, C.POINTER(_i64), _p, _p, _p, _p, _p, _i64, _i64, _p],
     "wdgh_spmm_structure_fused": [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _i32, _p,
                                   C.POINTER(_i64), _p, _p, _p, _p, _p, _p, _i64, _i64, _p],

@@ -246,28 +246,32 @@ def heavy_flags(g: CSRGraph):
 
 
 def spmm_ranged(g: CSRGraph, range_begin, range_end, x, y, norm, add_self_loop, dinv, deg_code, skip_rows,
-                accumulate, finalize, run_split_rows, x_row0=0, extra=(), extra_split=0):
+                accumulate, finalize, run_split_rows, x_row0=0, extra=None, extra_split=0, ctas_per_sm=0):
     """One phase of the aggregation: entries [range_begin[r], range_end[r]) of every row (see wdgh_spmm_csr_ranged).
 
     x_row0: global node id of x[0] -- lets a phase that only touches columns [x_row0, x_row0 + len(x)) read a
     feature shard in place (the kernel is handed the address x[0] would have at global id 0).
-    extra: raw partial sums of the same rows ([n, d] tensors, possibly peer-mapped) added as each row is stored;
-    the split-row pass adds only the last `extra_split` of them.  y may be a raw device address (peer memory)."""
+    extra: [parts, rows >= n, d] tensor of raw partial sums of the same rows (possibly peer-mapped), added to every row
+    as it is aggregated; the split-row pass adds only the last `extra_split` parts.  y may be peer memory.
+    ctas_per_sm: 0 = default grid, smaller = leave room for a kernel running concurrently on another stream."""
     d = int(x.shape[1])
     x_ptr = x.data_ptr() - int(x_row0) * x.stride(0) * 4
     plan, plan_host = g.plan
     partial = _partial_scratch(g, d)
-    arr, ld_extra = None, 0
-    if extra:
-        ld_extra = int(extra[0].stride(0))
-        assert all(int(e.stride(0)) == ld_extra and e.shape[0] >= g.n and e.shape[1] == d for e in extra)
-        arr = C.cast((C.c_void_p * len(extra))(*[e.data_ptr() for e in extra]), C.c_void_p)
+    n_extra = part_rows = ld_extra = 0
+    if extra is not None:
+        if extra.dim() != 3 or extra.shape[1] < g.n or extra.shape[2] != d or extra.stride(2) != 1:
+            raise ValueError("extra partial sums must be a [parts, rows >= n, d] tensor")
+        n_extra, ld_extra = int(extra.shape[0]), int(extra.stride(1))
+        if n_extra > 1 and extra.stride(0) % ld_extra:
+            raise ValueError("the parts of `extra` must be a whole number of rows apart")
+        part_rows = int(extra.stride(0)) // ld_extra if n_extra > 1 else int(extra.shape[1])
     check(lib.wdgh_spmm_csr_ranged(ptr(g.rowptr), ptr(range_begin), ptr(range_end), ptr(g.col), ptr(g.val), g.n,
                                    x_ptr, d, x.stride(0), ptr(y), y.stride(0), norm, int(bool(add_self_loop)),
                                    ptr(dinv), ptr(deg_code), ptr(skip_rows), int(bool(accumulate)), int(bool(finalize)),
-                                   int(bool(run_split_rows)), arr, len(extra), int(extra_split), ld_extra,
-                                   ptr(plan), plan_host, ptr(partial), g.row_offset, stream_ptr()),
-          "wdgh_spmm_csr_ranged")
+                                   int(bool(run_split_rows)), ptr(extra), n_extra, int(extra_split), part_rows,
+                                   ld_extra, int(ctas_per_sm), ptr(plan), plan_host, ptr(partial), g.row_offset,
+                                   stream_ptr()), "wdgh_spmm_csr_ranged")
     return y
 
 

@@ -360,15 +360,19 @@ class Cuda2DShardedStats:
       2. under the pull: degree scales, label pass, and the own row slice over the columns of the OWN shard
          (raw partial sums into receive slot 0);
       3. the pc - 1 foreign row slices, full column range: the aggregation kernel stores every finished row straight
-         into its owner's receive slot over NVLink (peer-mapped memory) -- compute and transfer are one kernel;
+         into its owner's receive slot over NVLink (peer-mapped memory) -- compute and transfer are one kernel.  These
+         launches are NVLink-bound from pc = 4 on, so (overlap=True) they run on half of the CTA slots while the own
+         slice's partner-shard columns are aggregated next to them on a second stream (`y +=` into slot 0);
       4. a tiny all-reduce orders the peers' stores before
-      5. the own row slice over the columns of the PARTNER shard, which adds slot 0 and the pc - 1 slices received
-         from the peers as every row is stored and applies self loop + scale: the last aggregation phase IS the
-         reduction and the epilogue (no separate reduce pass, no local copy of the foreign partials);
+      5. the last launch on the own slice: slot 0 and the pc - 1 slices received from the peers enter every row's
+         entry stream as virtual trailing entries next to the self loop, then the scale is applied -- with overlap the
+         column range is empty and the launch is a pure streaming reduction, without it the launch also aggregates the
+         partner-shard columns.  No separate reduce kernel, no local copy of the foreign partials;
       6. all-reduce of the class histograms + counters.
     Per rank 1 + (pc - 1) shards cross NVLink in each direction instead of N - 1."""
 
-    def __init__(self, grid: Grid2D, rank: int, slice_graphs, graph_1d, x_local, labels32_local, num_classes, group=None):
+    def __init__(self, grid: Grid2D, rank: int, slice_graphs, graph_1d, x_local, labels32_local, num_classes, group=None,
+                 overlap=None, foreign_ctas_per_sm=16, own_ctas_per_sm=16):
         from . import graph as G
         import torch.distributed._symmetric_memory as symm_mem
         if grid.pr != 2:
@@ -400,8 +404,10 @@ class Cuda2DShardedStats:
             self.partner * blk:(self.partner + 1) * blk]
         self._peer_recv = {r: self._hr.get_buffer(r, (pc, blk, d), torch.float32)
                            for r in grid.row_group_ranks(self.i) if r != rank}
-        self._copy = torch.cuda.Stream()
-        self._ev_ready, self._ev_x = torch.cuda.Event(), torch.cuda.Event()
+        self._copy, self._side = torch.cuda.Stream(), torch.cuda.Stream()
+        self._ev_ready, self._ev_x, self._ev_side = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.overlap = (pc >= 4) if overlap is None else (bool(overlap) and pc > 1)
+        self._ctas = (int(foreign_ctas_per_sm), int(own_ctas_per_sm))
         self._tiny = torch.zeros(1, dtype=torch.int32, device=dev)
         self._scratch = None
         self._y = torch.empty((self.g1d.n, d), dtype=torch.float32, device=dev)
@@ -451,25 +457,35 @@ class Cuda2DShardedStats:
         self._mark(marks, "own slice, own columns")
         cur.wait_event(self._ev_x)
         self._mark(marks, "wait pull")
+        rb, re = (g_own.rowptr[:-1], lo) if self.i == 1 else (hi, g_own.rowptr[1:])   # the partner shard's columns
+        if self.overlap:
+            # own slice, partner columns (HBM-bound) next to the NVLink-bound foreign slices, each on part of the SMs
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                G.spmm_ranged(g_own, rb, re, self.x_full, self.recv[0], norm, add_self_loop, dinv_full, code_full,
+                              self._skip[j], accumulate=True, finalize=False, run_split_rows=False,
+                              ctas_per_sm=self._ctas[1])
+                self._ev_side.record(self._side)
         # 3. foreign slices: rows leave for their owner as they are finished
         for k, s, owner in grid.schedule(r)[:-1]:
             g = self.slices[s]
             G.spmm_ranged(g, g.rowptr[:-1], g.rowptr[1:], self.x_full, self._peer_recv[owner][k], norm, add_self_loop,
-                          dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True)
+                          dinv_full, code_full, self._skip[s], accumulate=False, finalize=False, run_split_rows=True,
+                          ctas_per_sm=self._ctas[0] if self.overlap else 0)
             self._mark(marks, f"slice {s} -> rank {owner}")
+        if self.overlap:
+            cur.wait_event(self._ev_side)
+            self._mark(marks, "own slice, partner columns (second stream)")
         # 4. every rank's stores have landed once this all-reduce completes (stream-ordered after the kernels)
         if pc > 1:
             dist.all_reduce(self._tiny, group=self.group)
             self._mark(marks, "barrier")
-        # 5. own slice, partner columns + slot 0 + received slices + self loop + scale
-        if self.i == 1:   # partner shard lies below mine in the column order
-            rb, re = g_own.rowptr[:-1], lo
-        else:
-            rb, re = hi, g_own.rowptr[1:]
+        # 5. slot 0 + received slices + self loop + scale (+ the partner columns when they were not overlapped)
+        if self.overlap:
+            rb = re = g_own.rowptr[:-1]
         G.spmm_ranged(g_own, rb, re, self.x_full, self._y, norm, add_self_loop, dinv_full, code_full, self._skip[j],
-                      accumulate=False, finalize=True, run_split_rows=True,
-                      extra=[self.recv[k] for k in range(pc)], extra_split=pc - 1)
-        self._mark(marks, "own slice, partner columns + reduce + finalize")
+                      accumulate=False, finalize=True, run_split_rows=True, extra=self.recv, extra_split=pc - 1)
+        self._mark(marks, "own slice: " + ("" if self.overlap else "partner columns + ") + "reduce + finalize")
         counters, node_sum = ShardedStats.reduce_counters(self, self._scratch[0], self._scratch[1])
         if marks is not None:
             self._mark(marks, "counter all-reduce")
