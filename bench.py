@@ -176,6 +176,24 @@ class ClockSampler:
         return self.parse(text, t0, t1)
 
 
+def nvlink_bytes(device):
+    """(tx, rx) bytes this GPU has moved over NVLink so far, summed over its links (`nvidia-smi nvlink -gt d`); None
+    when the counters are not available."""
+    import re
+    try:
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", sel], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+        rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        if not tx or not rx:
+            return None
+        return sum(tx) * 1024, sum(rx) * 1024
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------
 # the CPU arm: the reference's own CPU implementation of the path on the host cores
 # ---------------------------------------------------------------------------
@@ -508,6 +526,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         counters, node_sum = step()
     barrier()
+    nvl0 = nvlink_bytes(device) if world > 1 and rank == 0 else None   # hardware NVLink counters around the timed steps
     launches0 = W.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -516,6 +535,7 @@ def main():
     ev1.record()
     barrier()
     t_load1 = time.time()
+    nvl1 = nvlink_bytes(device) if nvl0 is not None else None
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = W.launch_count() - launches0
     clocks = sampler.stop(t_load0, t_load1)
@@ -637,6 +657,19 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": spmm_ms, "algorithmic_bytes": alg_bytes, "share_of_step": spmm_ms / ms}
 
+    # ---- NVLink: bytes per step from the hardware counters of rank 0's GPU next to what the partition predicts ----
+    nvlink = None
+    if world > 1:
+        shard_bytes = part.block * d * 4
+        expect = ((1 + (world // 2 - 1)) if use_2d else (world - 1)) * shard_bytes    # per direction and step
+        nvlink = {"expected_bytes_per_direction_per_step": int(expect),
+                  "expected_gbs_over_step": expect / (ms * 1e-3) / 1e9,
+                  "reference_peer_copy_gbs": 770.0, "note": "B200_PROFILING.md: measured peer copy 770 GB/s per direction"}
+        if nvl0 is not None and nvl1 is not None:
+            tx, rx = (nvl1[0] - nvl0[0]) / args.steps, (nvl1[1] - nvl0[1]) / args.steps
+            nvlink.update(tx_bytes_per_step=tx, rx_bytes_per_step=rx, tx_gbs_over_step=tx / (ms * 1e-3) / 1e9,
+                          rx_gbs_over_step=rx / (ms * 1e-3) / 1e9, source="nvidia-smi nvlink -gt d, rank 0's GPU")
+
     # ---- metrics of the last step (sanity; also proves the counters left the device) ----------------
     h = counters.cpu().numpy()
     metrics = {"edge_homophily_with_self_loops": float((h[0] + n) / (nnz + n)),
@@ -678,7 +711,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, nnz),
                 "roofline": roofline, "roofline_labels": roofline_labels, "roofline_gram": roofline_gram,
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "metrics": metrics, "verify": verify}
+                "clocks": clocks, "metrics": metrics, "verify": verify, "nvlink": nvlink,
+                "stage_ms": getattr(pipe, "stage_ms", None)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

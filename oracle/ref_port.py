@@ -549,7 +549,7 @@ def plot_kr_metric(features, adj_dense, labels, sample_max, base_classifier="ker
                      z=torch.mm(a, x))
 
 
-def kr_unstable_nodes(gram, n_layers, tr, va, onehot_tr, rel=3e-7, trials=12, seed=0):
+def kr_unstable_nodes(gram, n_layers, tr, va, onehot_tr, rel=5e-7, rel_k=2e-6, trials=16, seed=0):
     """Validation nodes whose kernel-regression arg-max is decided by rounding noise.
 
     gram: the float32 Gram matrix of one epoch (Z Z^T of the sampled rows, before the arccos transform); tr / va:
@@ -558,26 +558,30 @@ def kr_unstable_nodes(gram, n_layers, tr, va, onehot_tr, rel=3e-7, trials=12, se
     default rcond = 1e-15, i.e. singular values down to 1e-15 of the largest are inverted: rounding noise of the Gram
     matrix passes through `sqrt(norm^2 - g^2)` (which cancels wherever two rows are nearly parallel) and is then
     amplified by the condition number of the train block.  A node is reported unstable when its arg-max changes under
-    any of `trials` symmetric perturbations G_ij += rel * sqrt(G_ii G_jj) * N(0, 1) -- the size of the float32
-    dot-product error bound (a few ulps of |z_i| |z_j|), which is what a different summation order or a different
-    float32 GEMM produces.  Returns a boolean tensor over the validation nodes.
+    any of `trials` symmetric perturbations of either kind:
+      * G_ij += rel * sqrt(G_ii G_jj) * N(0, 1) -- the size of the float32 dot-product error bound (a few ulps of
+        |z_i| |z_j|), which is what a different summation order of A X or of the Gram GEMM produces;
+      * K_ij *= 1 + rel_k * N(0, 1) on the transformed kernel -- what a differently rounded acos / sqrt produces
+        (the reference's own float32 transform is ~3e-5 away from its float64 evaluation).
+    Returns a boolean tensor over the validation nodes.
     """
     gen = torch.Generator().manual_seed(seed)
     gram = gram.to(torch.float32)
     d = torch.sqrt(torch.diag(gram).clamp(min=0))
     scale = d.reshape(-1, 1) * d.reshape(1, -1)
 
-    def predict(gm):
-        km = _arccos_kernel(gm, n_layers) / 2
+    def predict_k(km):
         ktt, kvt = km[tr][:, tr], km[va][:, tr]
         return (kvt @ (torch.tensor(np.linalg.pinv(ktt.numpy())) @ onehot_tr)).max(1)[1]
 
-    base = predict(gram)
+    k0 = _arccos_kernel(gram, n_layers) / 2
+    base = predict_k(k0)
     unstable = torch.zeros(base.shape[0], dtype=torch.bool)
     for _ in range(trials):
         e = torch.randn(gram.shape, generator=gen)
         e = (e + e.T) / 2 ** 0.5
-        unstable |= predict(gram + rel * scale * e) != base
+        unstable |= predict_k(_arccos_kernel(gram + rel * scale * e, n_layers) / 2) != base
+        unstable |= predict_k(k0 * (1 + rel_k * e)) != base
     return unstable
 
 

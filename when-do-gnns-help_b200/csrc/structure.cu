@@ -1031,8 +1031,8 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   // default: stream kernel with the per-node reductions folded in
   const bool stream_form = labels8 != nullptr && (size_t)(C + 1) * (C + 1) <= (size_t)kHistSmemBins &&
                            n + row_offset < (int64_t)INT32_MAX;
-  static const bool old_stream = getenv("WDGH_LABEL_OLD_STREAM") != nullptr;   // TEMPORARY A/B switch (one experiment)
-  if (stream_form && old_stream) {
+  static const bool runs_form = getenv("WDGH_LABEL_RUNS") != nullptr;   // TEMPORARY A/B switch (one experiment)
+  if (stream_form && !runs_form) {
     const size_t smem = ((size_t)(C + 1) * (C + 1) + 2 * (size_t)(C + 1)) * sizeof(unsigned);
     structure_stream_kernel<<<persistent_grid(ceil_div(n_groups, 8), 3), 256, smem, st>>>(
         rowptr, col, n, labels8, C, threshold, cnt, node_sum, deg_nsl, match_nsl, row_offset, sched);
