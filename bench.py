@@ -185,9 +185,11 @@ def nvlink_bytes(device):
         sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
         out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", sel], capture_output=True, text=True,
                              timeout=20).stdout
-        tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
-        rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        tx = [int(v) for v in re.findall(r"Tx:\s*(\d+)\s*KiB", out)]
+        rx = [int(v) for v in re.findall(r"Rx:\s*(\d+)\s*KiB", out)]
         if not tx or not rx:
+            if os.environ.get("WDGH_STAGE_TIMES") == "1":
+                print("[nvlink] unparsed nvidia-smi output: " + out[:400].replace("\n", " | "), file=sys.stderr)
             return None
         return sum(tx) * 1024, sum(rx) * 1024
     except Exception:
@@ -525,8 +527,8 @@ def main():
     t_load0 = time.time()             # clock samples are kept from here (warm-up + timed steps, all under load)
     for _ in range(max(args.warmup, 3)):
         counters, node_sum = step()
-    barrier()
     nvl0 = nvlink_bytes(device) if world > 1 and rank == 0 else None   # hardware NVLink counters around the timed steps
+    barrier()                         # (read BEFORE the barrier: nvidia-smi takes ~0.1-0.5 s on rank 0)
     launches0 = W.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
