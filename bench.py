@@ -362,6 +362,40 @@ def linkx_flow(hm, uf, row, col, labels, features, n, to_dev, epochs):
     return out
 
 
+def linkx_kr_check(hm, row, col, labels, features, n, device, epochs=3):
+    """The KR p-value is a t-test over per-epoch accuracies of kernel regressions whose train Gram is rank-deficient
+    (d = 7) and fed to pinv(rcond=1e-15): single predictions are decided by float32 rounding noise, so the p-value of two
+    float32 implementations may differ while every well-determined prediction agrees.  This is the per-prediction
+    contract of tests/test_gpu_parity.py::kr_contract on this workload (checker, untimed): same seeds through the CUDA
+    path and the oracle port, predictions compared node by node, flips allowed only on nodes the oracle's perturbation
+    analysis (oracle.kr_unstable_nodes) flags as noise-decided."""
+    import random
+    from oracle import ref_port as O
+    a_raw = torch.sparse_coo_tensor(torch.stack([row, col]), torch.ones(row.shape[0]), (n, n)).coalesce()
+    random.seed(11), np.random.seed(11), torch.manual_seed(11)
+    tr = []
+    hm.classifier_based_performance_metric(features.to(device), a_raw.to(device), labels, 500,
+                                           base_classifier="kernel_reg1", epochs=epochs, _trace=tr)
+    random.seed(11), np.random.seed(11), torch.manual_seed(11)
+    rtr = []
+    O.kr_metric(features.numpy(), row.numpy(), col.numpy(), np.ones(row.shape[0], np.float32), n, labels.numpy(), 500,
+                "kernel_reg1", epochs, trace=rtr)
+    out = {"epochs": epochs, "predictions": 0, "flips": 0, "unstable_predictions": 0, "flips_outside_unstable": 0}
+    for got, ref in zip(tr, rtr):
+        if not torch.equal(got["va"].cpu(), ref["va"]):
+            out["flips_outside_unstable"] += 1 << 20     # different validation sets: not comparable, flag loudly
+            continue
+        for side, kname in (("pred_g", "gram_g"), ("pred_x", "gram_x")):
+            changed = got[side].cpu() != ref[side]
+            unstable = O.kr_unstable_nodes(ref[kname], ref["n_layers"], ref["tr"], ref["va"], ref["onehot_tr"])
+            out["predictions"] += int(changed.numel())
+            out["flips"] += int(changed.sum())
+            out["unstable_predictions"] += int(unstable.sum())
+            out["flips_outside_unstable"] += int((changed & ~unstable).sum())
+    out["ok"] = out["flips_outside_unstable"] == 0
+    return out
+
+
 def run_linkx(args):
     """One JSON line: seconds per complete flow on the CUDA path, the reference's CPU seconds next to it."""
     import random
@@ -440,7 +474,8 @@ def run_linkx(args):
             "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * len(vals),
                     "note": "the flow starts from host tensors (as homophily_tests.py does) and ends with host scalars: "
                             "value IS the end-to-end time, host-side pinv / t-test / sampling included"},
-            "gpu_launches": int((W.launch_count() - launches0) // steps), "metrics": vals}
+            "gpu_launches": int((W.launch_count() - launches0) // steps), "metrics": vals,
+            "kr_check": linkx_kr_check(hm, row, col, labels, features, n, device)}
     print(json.dumps(line), flush=True)
 
 

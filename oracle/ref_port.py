@@ -407,6 +407,27 @@ def similarity(features, row, col, val, n, label_onehot, hard=None, LP=1, ifsum=
     return np.float32((((w - w * label).max(1)[0] <= 0.0) & ((w * label).sum(1) >= 0)).float().mean().item())
 
 
+
+def similarity_near_ties(features, row, col, val, n, label_onehot, rel=1e-6):
+    """Checker helper (not in the reference): number of nodes whose soft-LAS decision of `similarity` / `plot_similarity`
+    (hard=None, LP=1, ifsum=1: ratio >= 1, hm.py:216-218 / hp.py:226-228) is a TIE in exact arithmetic -- |ratio - 1|
+    <= rel with everything evaluated in float64.  For such a node the float32 outcome is decided by the summation order
+    of the Gram and of the class sums (torch's CPU sgemm / vectorised sum vs any other order), so a comparison of two
+    float32 implementations may differ by up to this many indicator flips; every other node must agree."""
+    x = torch.as_tensor(np.ascontiguousarray(features), dtype=torch.float64)
+    idx = torch.from_numpy(np.vstack([row, col]).astype(np.int64))
+    a = torch.sparse_coo_tensor(idx, torch.as_tensor(np.asarray(val, dtype=np.float64)), (n, n)).coalesce().to_dense()
+    z = a @ x
+    inner = z @ z.T
+    lab = torch.as_tensor(np.asarray(label_onehot)).argmax(1)
+    c = int(lab.max()) + 1
+    w = torch.stack([inner[:, lab == i].sum(1) for i in range(c)], 1)
+    own = w[torch.arange(n), lab]
+    degs = torch.bincount(lab, minlength=c)[lab].double()
+    ratio = (own / degs) / ((w.sum(1) - own) / (n - degs))
+    return int(((ratio - 1).abs() <= rel).sum().item())
+
+
 def _arccos_kernel(gram, n_layers, eps=1e-8):
     """One half of gntk_homophily_ (homophily_metrics.py:236-244 / 247-255)."""
     d = torch.sqrt(torch.diag(gram))

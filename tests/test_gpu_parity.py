@@ -709,9 +709,13 @@ def test_2d_partition_replay_on_one_gpu(W, d, world, n):
     assert n_heavy > 0
 
 
-@pytest.mark.parametrize("d,chunks_note", [(128, "pipelined"), (96, "single copy")])
+@pytest.mark.parametrize("d,chunks_note", [(128, "two 64-wide column blocks, Y back under the X copies"),
+                                           (192, "three column blocks"),
+                                           (160, "not a multiple of 64: row blocks, one phase per arriving block"),
+                                           (96, "single copy, then one launch")])
 def test_pipeline_host_entry(W, d, chunks_note):
-    """wdgh_pipeline_host (the e2e entry, host pointers in / counters + Y out) against the resident path."""
+    """wdgh_pipeline_host (the e2e entry, host pointers in / counters + Y out) against the resident path, every form
+    of its copy / compute pipeline (csrc/pipeline_host.cu)."""
     import ctypes as C
     lib = W._lib.lib
     n, c = 50000, 7

@@ -81,7 +81,7 @@ def main():
     worst = {k: 0.0 for k in TOL}
     kr = {"epochs_compared": 0, "epochs_identical": 0, "flips": 0, "flips_outside_unstable": 0}
     t_gpu = t_cpu = 0.0
-    n_graphs, bad = 0, []
+    n_graphs, bad, near_ties_total = 0, [], 0
     launches0 = W.launch_count()
     for key, ei, labels in graphs(archive, args.limit):
         n = labels.shape[0]
@@ -134,7 +134,14 @@ def main():
             O.plot_kr_metric(x, a, labels, args.kr_sample_max, clf, args.kr_epochs, trace=ref_traces[clf])
         t_cpu += time.perf_counter() - t0
         # ---------------- compare (not timed) ----------------
+        # soft LAS is a mean of per-node indicators `ratio >= 1`; on these graphs some nodes sit on an EXACT tie (e.g. one
+        # neighbour of every class: ratio = 1 in exact arithmetic), where float32 rounding decides.  Those nodes are
+        # counted in float64 and may flip, every other node must agree (1.5 / n on top, as in the golden tests).
+        near = O.similarity_near_ties(oh, row, col, val, n, oh)
+        near_ties_total += near
         for k, tol in TOL.items():
+            if k == "soft_las":
+                tol = tol + near / n
             # label informativeness is 2 - ratio with the ratio near 2 at low h: absolute, like the golden tests (1e-5)
             dev = abs(got[k] - ref[k]) / (1.0 if k == "soft_las" else 0.1 if k == "label_info" else max(abs(ref[k]), 1e-3))
             worst[k] = max(worst[k], dev)
@@ -162,7 +169,7 @@ def main():
     line = {"sweep": "data_synthesis (synthetic_plot.py:60-110)", "graphs": n_graphs, "kr_epochs": args.kr_epochs,
             "gpu_path_wall_s": round(t_gpu, 3), "cpu_oracle_wall_s": round(t_cpu, 3),
             "speedup_wall": round(t_cpu / max(t_gpu, 1e-9), 2), "worst_relative_deviation": worst, "tolerance": TOL,
-            "kr": kr, "gpu_launches": int(W.launch_count() - launches0), "violations": [str(b) for b in bad[:10]],
+            "soft_las_exact_tie_nodes": near_ties_total, "kr": kr, "gpu_launches": int(W.launch_count() - launches0), "violations": [str(b) for b in bad[:10]],
             "ok": not bad,
             "note": "both walls include the host-side parts the reference keeps on the host (pinv, t-test, RNG); "
                     "2000-node graphs are launch- and host-bound, not bandwidth-bound"}

@@ -9,6 +9,14 @@
 // per arriving block, the entries whose source node lies in that block (wdgh_spmm_csr_ranged:
 // column ranges of every row, y +=, self loop + scale with the last block).  Only the last
 // block's phase is exposed after the copies end.
+//
+// When Y = A_hat X has to come back to the host as well (y_host != NULL) the D2H copy of Y would follow the whole
+// H2D stream -- Y depends on every feature ROW block -- and the step would cost H2D + D2H back to back (1070 ms for
+// 30.1 + 25.6 GB).  PCIe is full duplex, and a COLUMN block of Y needs only the same column block of X, so this form
+// splits the feature matrix by columns instead: pitched copies (cudaMemcpy2DAsync, 256-byte rows out of the 512-byte
+// pitch keep the full link rate: 55.6 / 53.5 GB/s alone, 48 + 50 GB/s both directions at once, tools/pcie_probe.cu),
+// one full-graph aggregation launch per column block on strided views (ldx = ldy = d; bit-identical to the one-launch
+// result, tools/colblock_probe.py), and the D2H copy of block k runs under the H2D copy of block k + 1.
 #include <stdlib.h>
 
 #include <mutex>
@@ -29,13 +37,15 @@ struct HostPipelineCache {
   double *node_sum = nullptr;
   int64_t *seg = nullptr, *bounds = nullptr;  // column segments of the feature row blocks
   uint8_t *skip = nullptr;
-  cudaStream_t st = nullptr, st_copy = nullptr;
-  cudaEvent_t ev_csr = nullptr, ev_x[64] = {nullptr};
+  cudaStream_t st = nullptr, st_copy = nullptr, st_back = nullptr;
+  cudaEvent_t ev_csr = nullptr, ev_x[64] = {nullptr}, ev_y[64] = {nullptr};
   void release() {
     cudaFree(seg); cudaFree(bounds); cudaFree(skip);
     if (st_copy) cudaStreamDestroy(st_copy);
+    if (st_back) cudaStreamDestroy(st_back);
     if (ev_csr) cudaEventDestroy(ev_csr);
     for (auto &e : ev_x) if (e) cudaEventDestroy(e);
+    for (auto &e : ev_y) if (e) cudaEventDestroy(e);
     cudaFree(rowptr); cudaFree(col); cudaFree(x); cudaFree(y); cudaFree(dinv); cudaFree(partial);
     cudaFree(labels); cudaFree(labels8); cudaFree(deg_code); cudaFree(deg); cudaFree(match); cudaFree(plan); cudaFree(counters); cudaFree(node_sum);
     if (st) cudaStreamDestroy(st);
@@ -55,6 +65,19 @@ static int e2e_chunks() {
     cached = (v >= 1 && v <= 64) ? v : 16;
   }
   return cached;
+}
+
+// Width (floats) of the column blocks of the Y-returning form, 0 = row-block form.  64 floats = 256-byte rows: the
+// narrowest pitched copy that still runs at the full PCIe rate in both directions (128-byte rows: 34 + 40 GB/s), and a
+// width the row-group aggregation kernel runs natively.  WDGH_E2E_COLW overrides (0, 32 or 64).
+static int64_t e2e_col_width(int64_t d) {
+  static int cached = -1;
+  if (cached < 0) {
+    int v = 64;
+    if (const char *e = getenv("WDGH_E2E_COLW")) v = atoi(e);
+    cached = (v == 0 || v == 32 || v == 64) ? v : 64;
+  }
+  return (cached > 0 && d % cached == 0 && d / cached >= 2 && d / cached <= 64) ? cached : 0;
 }
 
 }  // namespace wdgh
@@ -97,25 +120,35 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMalloc(&c.counters, n_counters * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.node_sum, 2 * sizeof(double)));
     WDGH_CUDA(cudaStreamCreateWithFlags(&c.st_copy, cudaStreamNonBlocking));
+    WDGH_CUDA(cudaStreamCreateWithFlags(&c.st_back, cudaStreamNonBlocking));
     WDGH_CUDA(cudaEventCreateWithFlags(&c.ev_csr, cudaEventDisableTiming));
     for (int k = 0; k < 64; ++k) WDGH_CUDA(cudaEventCreateWithFlags(&c.ev_x[k], cudaEventDisableTiming));
+    for (int k = 0; k < 64; ++k) WDGH_CUDA(cudaEventCreateWithFlags(&c.ev_y[k], cudaEventDisableTiming));
     WDGH_CUDA(cudaMalloc(&c.seg, (size_t)(e2e_chunks() + 1) * (size_t)n * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.bounds, 65 * sizeof(int64_t)));
     WDGH_CUDA(cudaMalloc(&c.skip, (size_t)n));
     c.n = n; c.nnz = nnz; c.d = d; c.C = C; c.cap = cap; c.device = device;
   }
-  cudaStream_t st = c.st, sc = c.st_copy;
+  cudaStream_t st = c.st, sc = c.st_copy, sb = c.st_back;
   const bool ranged_ok = (d % 4 == 0) && (d >= 128 || d == 64 || d == 32);
-  const int K = ranged_ok ? e2e_chunks() : 1;
+  const int64_t colw = y_host ? e2e_col_width(d) : 0;   // > 0: column-block form (Y travels back under the X copies)
+  const int KC = colw ? (int)(d / colw) : 0;
+  const int K = colw ? KC : (ranged_ok ? e2e_chunks() : 1);
   // 1. graph + labels first (the compute stream needs them at once) ...
   WDGH_CUDA(cudaMemcpyAsync(c.rowptr, rowptr_host, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sc));
   if (nnz) WDGH_CUDA(cudaMemcpyAsync(c.col, col_host, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
   WDGH_CUDA(cudaMemcpyAsync(c.labels, labels_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
   WDGH_CUDA(cudaEventRecord(c.ev_csr, sc));
-  // 2. ... then the feature matrix, row block by row block, on the copy stream
+  // 2. ... then the feature matrix on the copy stream: column blocks (pitched) when Y goes back to the host,
+  //    row blocks otherwise
   const int64_t blk = (n + K - 1) / K;
   int64_t bounds_h[65];
-  for (int k = 0; k < K; ++k) {
+  for (int k = 0; k < KC; ++k) {
+    WDGH_CUDA(cudaMemcpy2DAsync(c.x + k * colw, d * sizeof(float), x_host + k * colw, d * sizeof(float),
+                                colw * sizeof(float), n, cudaMemcpyHostToDevice, sc));
+    WDGH_CUDA(cudaEventRecord(c.ev_x[k], sc));
+  }
+  for (int k = 0; k < K && !colw; ++k) {
     const int64_t r0 = (int64_t)k * blk, r1 = (r0 + blk < n) ? r0 + blk : n;
     bounds_h[k] = r0;
     if (r1 > r0)
@@ -146,7 +179,19 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   rc = wdgh_structure_counts(c.rowptr, c.col, n, nnz, c.labels, C, c.plan, plan_host, c.counters, c.node_sum, c.deg,
                              c.match, c.labels8, n, 0, st);
   if (rc) return rc;
-  if (K == 1) {
+  if (colw) {
+    // 4'. one full-graph aggregation launch per arriving column block; its Y block leaves at once on the third stream
+    for (int k = 0; k < KC; ++k) {
+      WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[k], 0));
+      rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x + k * colw, colw, d, c.y + k * colw, d, norm, add_self_loop,
+                         dinv, code, c.plan, plan_host, c.partial, 0, st);
+      if (rc) return rc;
+      WDGH_CUDA(cudaEventRecord(c.ev_y[k], st));
+      WDGH_CUDA(cudaStreamWaitEvent(sb, c.ev_y[k], 0));
+      WDGH_CUDA(cudaMemcpy2DAsync(y_host + k * colw, d * sizeof(float), c.y + k * colw, d * sizeof(float),
+                                  colw * sizeof(float), n, cudaMemcpyDeviceToHost, sb));
+    }
+  } else if (K == 1) {
     WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[0], 0));
     rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x, d, d, c.y, d, norm, add_self_loop, dinv, code, c.plan,
                        plan_host, c.partial, 0, st);
@@ -168,7 +213,7 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     }
   }
   // Y leaves on the copy stream as soon as the last phase is done; the counters follow on the compute stream
-  if (y_host) {
+  if (y_host && !colw) {
     WDGH_CUDA(cudaEventRecord(c.ev_csr, st));
     WDGH_CUDA(cudaStreamWaitEvent(sc, c.ev_csr, 0));
     WDGH_CUDA(cudaMemcpyAsync(y_host, c.y, n * d * sizeof(float), cudaMemcpyDeviceToHost, sc));
@@ -186,6 +231,6 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
     WDGH_CUDA(cudaMemcpyAsync(node_sum_host, c.node_sum, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     WDGH_CUDA(cudaStreamSynchronize(st));
   }
-  if (y_host) WDGH_CUDA(cudaStreamSynchronize(sc));
+  if (y_host) WDGH_CUDA(cudaStreamSynchronize(colw ? sb : sc));
   return 0;
 }

@@ -261,7 +261,7 @@ structure_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__r
 // Split rows contribute no entries here (structure_chunks_kernel + structure_heavy_nodes_kernel own them).
 // ---------------------------------------------------------------------------
 constexpr int kStreamEPL = 4;
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 structure_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
                         const uint8_t *__restrict__ labels8, int C, int64_t threshold,
                         unsigned long long *__restrict__ counters, double *__restrict__ node_sum,
@@ -468,273 +468,6 @@ structure_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__res
   unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
   long long m_all = 0, m_lab = 0, n_lab = 0;
   for (int bin = threadIdx.x; bin < C1 * C1; bin += blockDim.x) {
-    const unsigned v = s_hist[bin];
-    if (v == 0) continue;
-    const int a = bin / C1, b2 = bin - a * C1;
-    if (a == b2) m_all += v;
-    if (a < C && b2 < C) {
-      n_lab += v;
-      if (a == b2) m_lab += v;
-      atomicAdd(&g_hist[a * C + b2], (unsigned long long)v);
-    }
-  }
-  m_all = warp_sum(m_all);
-  m_lab = warp_sum(m_lab);
-  n_lab = warp_sum(n_lab);
-  if (lane == 0) {
-    if (m_all) atomicAdd(&counters[WDGH_SC_MATCH_ALL], (unsigned long long)m_all);
-    if (m_lab) atomicAdd(&counters[WDGH_SC_MATCH_LAB], (unsigned long long)m_lab);
-    if (n_lab) atomicAdd(&counters[WDGH_SC_N_LAB], (unsigned long long)n_lab);
-  }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (s_cnt[c]) atomicAdd(&g_cls[c], (unsigned long long)s_cnt[c]);
-    if (s_deg[c]) atomicAdd(&g_cls[C + c], (unsigned long long)s_deg[c]);
-  }
-  sched_retire(sched, gridDim.x);
-}
-
-constexpr int kPrivBins = 128;        // lane-private pair counters: (C+1)^2 <= 128
-// ---------------------------------------------------------------------------
-// Run form of the edge pass (the default for 1-byte labels): every lane owns a RUN of 8 CONSECUTIVE stream
-// positions, so everything that is per-row -- which row an entry belongs to, the row's label, its slot -- is looked up
-// once per run instead of once per entry, and the eight column ids and eight label bytes of a lane are independent
-// loads in flight together.  ncu on the stream kernel above showed the pass instruction-bound (118 warp instructions
-// per 32 entries, 54% issue utilisation); here one warp iteration covers 256 entries:
-//   * row of a run: per 1024-position window the row owners set one bit per row START in a 32-word shared bitmap
-//     (one atomicOr each), a warp scan adds "rows started before this word"; the run's first row is one 8-byte
-//     shared load + popc, the rows that start INSIDE the run are the next 7 bits of the same word;
-//   * pair table over (C+1) x (C+1) label values (unlabelled = C, self loops excluded) from which the scalar counters
-//     are summed once per CTA; with (C+1)^2 <= 128 every lane owns private 32-bit counters in shared memory
-//     ([key][lane]: conflict-free, no atomics), larger tables use shared atomics;
-//   * per-row match counts: a lane counts the matches of its run in a register and adds them to the row's shared
-//     counter when the row changes or the run ends;
-//   * per-node reductions in the group epilogue, as in the stream kernel.
-// What is left per entry is the label gather itself: one 32-byte sector from L2 per stored entry (~2.6 ms at the
-// measured L2 sector rate for 976M entries) -- that, not the instruction count, bounds this kernel.
-// ---------------------------------------------------------------------------
-constexpr int kRun = 8;                 // consecutive stream positions per lane
-constexpr int kRunWarps = 4;            // warps per CTA
-constexpr int kRunWindow = 1024;        // stream positions per bitmap window (32 words)
-template <bool PRIV>
-__global__ void __launch_bounds__(32 * kRunWarps, 3)
-structure_runs_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n,
-                      const uint8_t *__restrict__ labels8, int C, int64_t threshold,
-                      unsigned long long *__restrict__ counters, double *__restrict__ node_sum,
-                      int32_t *__restrict__ deg_nsl, int32_t *__restrict__ match_nsl, int64_t row_offset,
-                      unsigned long long *__restrict__ sched) {
-  extern __shared__ unsigned s_dyn[];  // [(C+1)^2] pair table, [C+1] class sizes, [C+1] class degree mass, [PRIV: W x 128 x 32]
-  __shared__ int2 s_pack[kRunWarps][32];       // compacted non-empty rows: {(row slot << 8) | label, address correction}
-  __shared__ unsigned s_heads[kRunWarps][32];  // per window: bit = a row starts at this stream position
-  __shared__ int2 s_hb[kRunWarps][32];         // {start bits of the word, rows started before the word}
-  __shared__ int s_match[kRunWarps][32], s_selfc[kRunWarps][32];   // per row slot of the group
-  constexpr unsigned kFull = 0xffffffffu;
-  const int C1 = C + 1, nbins = C1 * C1;
-  unsigned *s_hist = s_dyn, *s_cnt = s_dyn + nbins, *s_deg = s_cnt + C1;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned *s_priv = s_deg + C1 + wid * (kPrivBins * 32) + lane;   // this lane's counters: s_priv[key * 32]
-  for (int b = threadIdx.x; b < nbins + 2 * C1 + (PRIV ? kRunWarps * kPrivBins * 32 : 0); b += blockDim.x) s_dyn[b] = 0;
-  __syncthreads();
-  const unsigned lanes_lt = (1u << lane) - 1u;
-  const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_groups = (n + 31) >> 5;
-  unsigned n_self = 0, n_self_lab = 0;                  // per lane
-  double sum = 0.0, sum_self = 0.0;                     // per lane (row owner)
-  unsigned n_nsl = 0, n_empty = 0;
-  long long nbins_seen = 0;
-
-  auto take = [&]() -> int64_t {
-    unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(&sched[0], 1ull);
-    return (int64_t)__shfl_sync(kFull, t, 0) + W;  // the first W groups are handed out by position
-  };
-  auto load_bounds = [&](int64_t g, int64_t &b, int64_t &e, int &li) {
-    b = 0;
-    e = 0;
-    li = C;
-    const int64_t r = (g << 5) + lane;
-    if (r < n) {
-      b = __ldg(rowptr + r);
-      e = __ldg(rowptr + r + 1);
-      const int v = __ldg(labels8 + r + row_offset);
-      li = (v == 255) ? C : v;
-    }
-  };
-
-  int64_t g = (int64_t)blockIdx.x * kRunWarps + wid;
-  if (g < n_groups) {
-    int64_t b, e, nb, ne;
-    int li, nli;
-    load_bounds(g, b, e, li);
-    int64_t gn = take();
-    load_bounds(gn, nb, ne, nli);  // the next group's bounds travel while this group is walked
-    while (true) {
-      // ---- scan the row lengths, publish the compacted row table ----
-      const int dall = (int)(e - b);                    // full row length (split rows included)
-      const int len = (e - b > threshold) ? 0 : dall;   // split rows count as empty here
-      int inc = len;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += v;
-      }
-      const int off = inc - len;
-      const int total = __shfl_sync(kFull, inc, 31);
-      const int64_t gbeg = __shfl_sync(kFull, b, 0);
-      const int32_t *cp = col + gbeg;
-      const unsigned ne_mask = __ballot_sync(kFull, len > 0);
-      if (len > 0) s_pack[wid][__popc(ne_mask & lanes_lt)] = make_int2((lane << 8) | li, (int)(b - gbeg) - off);
-      s_match[wid][lane] = 0;
-      s_selfc[wid][lane] = 0;
-      const int grow0 = (int)((g << 5) + row_offset);
-      for (int w0 = 0; w0 < total; w0 += kRunWindow) {
-        const int wlen = min(kRunWindow, total - w0);
-        // ---- window tables ----
-        s_heads[wid][lane] = 0;
-        __syncwarp();
-        const int rel = off - w0;
-        if (len > 0 && rel >= 0 && rel < kRunWindow) atomicOr(&s_heads[wid][rel >> 5], 1u << (rel & 31));
-        __syncwarp();
-        {
-          const unsigned hw = s_heads[wid][lane];
-          const int pc = __popc(hw);
-          int acc = pc;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(kFull, acc, o);
-            if (lane >= o) acc += v;
-          }
-          const int before = __popc(__ballot_sync(kFull, len > 0 && rel < 0));
-          s_hb[wid][lane] = make_int2((int)hw, before + acc - pc);
-        }
-        __syncwarp();
-        for (int p0 = 0; p0 < wlen; p0 += 32 * kRun) {
-          const int p = p0 + lane * kRun;             // first position of this lane's run (inside one bitmap word)
-          const int nvalid = min(kRun, wlen - p);     // <= 0: nothing to do for this lane
-          if (nvalid > 0) {
-            const int2 hb = s_hb[wid][p >> 5];
-            const int bit = p & 31;
-            int rank = hb.y + __popc((unsigned)hb.x & (kFull >> (31 - bit))) - 1;
-            // rows that start at positions p+1 .. p+nvalid-1 (same word: p is a multiple of 8)
-            const unsigned hbits = (((unsigned)hb.x >> bit) >> 1) & ((1u << (nvalid - 1)) - 1u);
-            int2 rec = s_pack[wid][rank];
-            const int2 rec_last = hbits ? s_pack[wid][rank + __popc(hbits)] : rec;
-            int j[kRun], lj[kRun];
-            if (rec_last.y == rec.y) {  // one address correction for the whole run (no split row in between)
-              const int32_t *q = cp + (w0 + p + rec.y);
-#pragma unroll
-              for (int t = 0; t < kRun; ++t) j[t] = (t < nvalid) ? __ldg(q + t) : -1;
-            } else {                    // rare: a split row lies between two rows of this run
-              int rk = rank;
-              int dl = rec.y;
-#pragma unroll
-              for (int t = 0; t < kRun; ++t) {
-                if (t > 0 && ((hbits >> (t - 1)) & 1u)) dl = s_pack[wid][++rk].y;
-                j[t] = (t < nvalid) ? __ldg(cp + (w0 + p + t + dl)) : -1;
-              }
-            }
-#pragma unroll
-            for (int t = 0; t < kRun; ++t) lj[t] = (j[t] >= 0) ? (int)__ldg(labels8 + (unsigned)j[t]) : 255;
-            int lie = rec.x & 0xff, slot = rec.x >> 8;
-            int cm = 0, cs = 0;
-#pragma unroll
-            for (int t = 0; t < kRun; ++t) {
-              if (t > 0 && ((hbits >> (t - 1)) & 1u)) {  // a new row starts here: hand the counts to the old one
-                if (cm) atomicAdd(&s_match[wid][slot], cm);
-                if (cs) atomicAdd(&s_selfc[wid][slot], cs);
-                cm = cs = 0;
-                rec = s_pack[wid][++rank];
-                lie = rec.x & 0xff;
-                slot = rec.x >> 8;
-              }
-              if (t < nvalid) {
-                const int ljx = (lj[t] == 255) ? C : lj[t];
-                if (j[t] == grow0 + slot) {            // stored diagonal entry
-                  cs += 1;
-                  n_self += 1;
-                  n_self_lab += (lie < C);
-                } else {
-                  const int key = lie * C1 + ljx;
-                  if (PRIV) s_priv[key << 5] += 1u;
-                  else atomicAdd(&s_hist[key], 1u);
-                  cm += (lie == ljx);
-                }
-              }
-            }
-            if (cm) atomicAdd(&s_match[wid][slot], cm);
-            if (cs) atomicAdd(&s_selfc[wid][slot], cs);
-          }
-        }
-        __syncwarp();  // the window tables are rebuilt
-      }
-      // ---- group epilogue: per-row outputs and the per-node reductions of the rows this warp owns ----
-      __syncwarp();
-      const int64_t r = (g << 5) + lane;
-      if (r < n) {
-        const bool heavy = dall > threshold;
-        const int my_match = s_match[wid][lane], my_self = s_selfc[wid][lane];
-        const int dn = len - my_self;
-        deg_nsl[r] = heavy ? 0 : dn;       // split rows: zero here, the chunk kernel adds atomically
-        match_nsl[r] = heavy ? 0 : my_match;
-        if (!heavy) {
-          if (dn > 0) {
-            sum += (double)((float)my_match / (float)dn);  // float32 division as torch does (hm.py:77)
-            n_nsl += 1;
-            nbins_seen = max(nbins_seen, (long long)(r + row_offset + 1));  // ticket order: not in row order
-          }
-          if (dall == 0) n_empty += 1;
-          else sum_self += (double)((float)(my_match + my_self) / (float)dall);  // homophily_plot.py:92-100
-          if (li < C) {
-            atomicAdd(&s_cnt[li], 1u);
-            atomicAdd(&s_deg[li], (unsigned)dall);
-            if (dn == 0) atomicAdd(&counters[WDGH_SC_HEADER + 2 * C + (size_t)C * C + li], 1ull);  // isolated: rare
-          }
-        }
-      }
-      __syncwarp();  // s_pack / s_match are rewritten by the next group
-      g = gn;
-      if (g >= n_groups) break;
-      b = nb; e = ne; li = nli;
-      gn = take();
-      load_bounds(gn, nb, ne, nli);
-    }
-  }
-  if (PRIV) {  // lane-private pair counters -> the CTA's pair table
-    __syncwarp();
-    for (int key = 0; key < nbins; ++key) {
-      const unsigned v = __reduce_add_sync(kFull, s_priv[key << 5]);
-      if (lane == 0 && v) atomicAdd(&s_hist[key], v);
-    }
-  }
-  // ---- per-warp scalars ----
-  {
-    const double s0 = warp_sum(sum), s1 = warp_sum(sum_self);
-    const long long q0 = warp_sum((long long)n_nsl), q1 = warp_sum((long long)n_empty);
-    const long long q2 = warp_sum((long long)n_self), q3 = warp_sum((long long)n_self_lab);
-    long long nbm = nbins_seen;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nbm = max(nbm, __shfl_xor_sync(kFull, nbm, o));
-    if (lane == 0) {
-      if (s0 != 0.0) atomicAdd(node_sum, s0);
-      if (s1 != 0.0) atomicAdd(node_sum + 1, s1);
-      if (q0) atomicAdd(&counters[WDGH_SC_N_NODES_NSL], (unsigned long long)q0);
-      if (q1) atomicAdd(&counters[WDGH_SC_N_EMPTY], (unsigned long long)q1);
-      if (nbm) atomicMax(&counters[WDGH_SC_NBINS], (unsigned long long)nbm);
-      if (q2) {
-        atomicAdd(&counters[WDGH_SC_N_SELF], (unsigned long long)q2);
-        atomicAdd(&counters[WDGH_SC_MATCH_ALL], (unsigned long long)q2);
-      }
-      if (q3) {
-        atomicAdd(&counters[WDGH_SC_MATCH_LAB], (unsigned long long)q3);
-        atomicAdd(&counters[WDGH_SC_N_LAB], (unsigned long long)q3);
-      }
-    }
-  }
-  // ---- per-CTA tables: the pair table also yields the scalar counters ----
-  __syncthreads();
-  unsigned long long *g_cls = counters + WDGH_SC_HEADER;
-  unsigned long long *g_hist = counters + WDGH_SC_HEADER + 2 * C;
-  long long m_all = 0, m_lab = 0, n_lab = 0;
-  for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
     const unsigned v = s_hist[bin];
     if (v == 0) continue;
     const int a = bin / C1, b2 = bin - a * C1;
@@ -1031,31 +764,13 @@ extern "C" int wdgh_structure_counts(const int64_t *rowptr, const int32_t *col, 
   // default: stream kernel with the per-node reductions folded in
   const bool stream_form = labels8 != nullptr && (size_t)(C + 1) * (C + 1) <= (size_t)kHistSmemBins &&
                            n + row_offset < (int64_t)INT32_MAX;
-  static const bool runs_form = getenv("WDGH_LABEL_RUNS") != nullptr;   // TEMPORARY A/B switch (one experiment)
-  if (stream_form && !runs_form) {
+  if (stream_form) {
     const size_t smem = ((size_t)(C + 1) * (C + 1) + 2 * (size_t)(C + 1)) * sizeof(unsigned);
-    structure_stream_kernel<<<persistent_grid(ceil_div(n_groups, 8), 3), 256, smem, st>>>(
+    // 4 CTAs / SM (64 registers, 76 B of spills): 5.89 ms on the 976M-entry graph against 6.16 ms at 3 CTAs / SM
+    // (76 registers, no spills) and 6.71 ms at 5 (48 registers)
+    structure_stream_kernel<<<persistent_grid(ceil_div(n_groups, 8), 4), 256, smem, st>>>(
         rowptr, col, n, labels8, C, threshold, cnt, node_sum, deg_nsl, match_nsl, row_offset, sched);
     WDGH_LAUNCHED("structure_stream_kernel");
-  } else if (stream_form) {
-    const size_t bins = (size_t)(C + 1) * (C + 1);
-    const size_t smem = (bins + 2 * (size_t)(C + 1)) * sizeof(unsigned);
-    const unsigned grid = persistent_grid(ceil_div(n_groups, kRunWarps), 3);
-    if (bins <= (size_t)kPrivBins) {  // lane-private pair counters: 16 KB per warp
-      const size_t smem_priv = smem + (size_t)kRunWarps * kPrivBins * 32 * sizeof(unsigned);
-      static bool configured = false;
-      if (!configured) {
-        WDGH_CUDA(cudaFuncSetAttribute(structure_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(smem_priv + 1024)));
-        configured = true;
-      }
-      structure_runs_kernel<true><<<grid, 32 * kRunWarps, smem_priv, st>>>(rowptr, col, n, labels8, C, threshold, cnt,
-                                                                          node_sum, deg_nsl, match_nsl, row_offset, sched);
-    } else {
-      structure_runs_kernel<false><<<grid, 32 * kRunWarps, smem, st>>>(rowptr, col, n, labels8, C, threshold, cnt,
-                                                                      node_sum, deg_nsl, match_nsl, row_offset, sched);
-    }
-    WDGH_LAUNCHED("structure_runs_kernel");
   } else if (labels8) {
     rc = launch_edge_rows<uint8_t>(rowptr, col, n, labels8, C, threshold, cnt, deg_nsl, match_nsl, hist_smem, st,
                                    row_offset, sched);
