@@ -692,7 +692,13 @@ def main():
                           + (": the pc row slices of this rank's block as raw partial sums, local stores" if use_2d else ""),
                 "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms": spmm_ms, "algorithmic_bytes": alg_bytes, "share_of_step": spmm_ms / ms}
+                "kernel_ms": spmm_ms, "algorithmic_bytes": alg_bytes, "share_of_step": spmm_ms / ms,
+                # DRAM bytes actually moved (ncu) / time / peak: stays below 1, whereas `frac` may exceed 1 slightly on a
+                # box that is not power-capped -- its numerator counts ~5% of L2-served bytes (degree codes, repeated
+                # feature rows) and its denominator is a read+write copy_, not the HBM pin rate (profiles/summary_r02.md)
+                "traffic_frac": (traffic / (spmm_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "traffic_source": "profiles/spmm_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum per stored "
+                                  "entry of this kernel on a 16M-node instance of the same generator, times this launch's entries"}
 
     # ---- NVLink: bytes per step from the hardware counters of rank 0's GPU next to what the partition predicts ----
     nvlink = None

@@ -10,7 +10,7 @@ Every rank builds its row shard of the bench generator's graph and runs, in this
     2d         2 row groups x N/2 column groups: partner shard pulled, foreign row slices stored into their owners'
                memory by the aggregation kernel, own slice finished by its last phase (reduce + self loop + scale)
     2d-overlap (N >= 4) the same with the own slice's partner columns aggregated NEXT TO the foreign slices on a
-               second stream and a pure streaming reduction as last launch (the default from N = 8 on)
+               second stream and a pure streaming reduction as last launch (opt-in: measured slower at N = 8)
     1d-plain   NCCL all-gather of the features, then ONE aggregation launch (the N = 1 kernel on a row shard)
 
 and compares each result (Y rows of the rank, all-reduced counters, node sum) with 1d-plain, which runs LAST so that
