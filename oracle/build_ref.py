@@ -10,6 +10,11 @@ install), so "building" it means taking the modules of the path, byte for byte, 
 
     /root/reference/utils/{homophily_metrics,util_funcs,homophily_plot,datasets}.py  ->  oracle/_ref/utils/
 
+For the drop-in demonstration (tools/run_reference_script.py: the reference's own `homophily_tests.py`, UNCHANGED, run
+against the wdgh_b200 mirrors) it also takes the script itself and the small dataset files its loader reads:
+
+    /root/reference/homophily_tests.py, data/ind.{cora,citeseer}.*, new_data/{texas,cornell,wisconsin}/out1_*.txt
+
 It also packs the 580 `data_synthesis/{800,4000}/<h>/adj_<h>_<s>.pt` graphs the reference ships (2000 nodes, 5 classes;
 the inputs of synthetic_plot.py:60-110) into ONE compressed archive, oracle/_ref/data_synthesis.npz, so that the sweep
 runner (tools/sweep_synthesis.py) can replay the whole sweep on the GPU box.
@@ -26,7 +31,10 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference"
 DST = os.path.join(HERE, "_ref")
-FILES = ["utils/homophily_metrics.py", "utils/util_funcs.py", "utils/homophily_plot.py", "utils/datasets.py"]
+FILES = ["utils/homophily_metrics.py", "utils/util_funcs.py", "utils/homophily_plot.py", "utils/datasets.py",
+         "homophily_tests.py"]
+DATA_GLOBS = ["data/ind.cora.*", "data/ind.citeseer.*", "new_data/texas/out1_*.txt", "new_data/cornell/out1_*.txt",
+              "new_data/wisconsin/out1_*.txt"]
 
 
 def pack_data_synthesis():
@@ -65,6 +73,13 @@ def build():
         src, dst = os.path.join(SRC, rel), os.path.join(DST, rel)
         shutil.copyfile(src, dst)
         manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
+    import glob
+    for pat in DATA_GLOBS:      # inputs of the reference's dataset loaders (uf.py:60-100, 288-330), as shipped
+        for src in sorted(glob.glob(os.path.join(SRC, pat))):
+            dst = os.path.join(DST, os.path.relpath(src, SRC))
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                shutil.copyfile(src, dst)
     with open(os.path.join(DST, "MANIFEST.json"), "w") as f:
         json.dump({"source": SRC, "sha256": manifest}, f, indent=1)
     pack_data_synthesis()
