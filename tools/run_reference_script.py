@@ -15,7 +15,8 @@ resolve to:
     its dataset loaders (`full_load_data_large`: file IO + networkx, out of scope of the hot path) stay -- with every
     function `wdgh_b200.util_funcs` mirrors replaced by the mirror.  This is the binding INTEGRATION.md describes.
 
-In both arms the SCRIPT (and the reference modules it imports) see `torch.cuda.is_available() == False`, i.e. the script
+In both arms the SCRIPT and the reference modules it imports (callers whose source file lies in the reference tree, nobody
+else) see `torch.cuda.is_available() == False`, i.e. the script
 follows its CPU path -- BASELINE.json configs[0], "homophily_tests.py on CPU (reference path)" -- and hands host tensors
 to whatever `utils.*` is bound; the mirrors move them to the B200 themselves (the library is initialised before the
 patch).  The script's own CUDA branch cannot be used for a comparison: it is broken upstream (edge_homo indexes a CPU
@@ -70,7 +71,13 @@ def bind(impl, tree):
     if impl == "wdgh":
         import wdgh_b200
         wdgh_b200._lib.require_device()        # needs the real torch.cuda.is_available(); cached afterwards
-    torch.cuda.is_available = lambda: False    # from here on the script and the reference modules take their CPU path
+    # from here on the script and the reference modules (every caller whose source file lies in `tree`) take their CPU
+    # path; torch's own internals and the mirrors keep seeing the real answer
+    real = torch.cuda.is_available
+
+    def is_available():
+        return False if sys._getframe(1).f_code.co_filename.startswith(tree) else real()
+    torch.cuda.is_available = is_available
     import utils.homophily_metrics  # noqa: F401
     import utils.util_funcs as ref_uf
     if impl == "reference":

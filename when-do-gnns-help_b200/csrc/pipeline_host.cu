@@ -15,8 +15,10 @@
 // 30.1 + 25.6 GB).  PCIe is full duplex, and a COLUMN block of Y needs only the same column block of X, so this form
 // splits the feature matrix by columns instead: pitched copies (cudaMemcpy2DAsync, 256-byte rows out of the 512-byte
 // pitch keep the full link rate: 55.6 / 53.5 GB/s alone, 48 + 50 GB/s both directions at once, tools/pcie_probe.cu),
-// one full-graph aggregation launch per column block on strided views (ldx = ldy = d; bit-identical to the one-launch
-// result, tools/colblock_probe.py), and the D2H copy of block k runs under the H2D copy of block k + 1.
+// aggregation of a column block on strided views (ldx = ldy = d; bit-identical to the one-launch result,
+// tools/colblock_probe.py) phased by arriving row chunk exactly like the counters-only form, so that only the last
+// chunk's phase separates the end of a block's H2D copy from the start of its D2H copy, and the D2H copy of block k
+// runs under the H2D copy of block k + 1.
 #include <stdlib.h>
 
 #include <mutex>
@@ -80,6 +82,19 @@ static int64_t e2e_col_width(int64_t d) {
   return (cached > 0 && d % cached == 0 && d / cached >= 2 && d / cached <= 64) ? cached : 0;
 }
 
+// Row chunks per column block of the Y-returning form: the block's aggregation is phased by arriving row chunk (as in
+// the counters-only form), so that only the last chunk's phase -- not a whole-graph launch -- stands between the end of
+// a block's H2D copy and the start of its D2H copy.  WDGH_E2E_COLROWS overrides (1 = one launch per column block).
+static int e2e_col_rows() {
+  static int cached = 0;
+  if (cached == 0) {
+    int v = 8;
+    if (const char *e = getenv("WDGH_E2E_COLROWS")) v = atoi(e);
+    cached = (v >= 1 && v <= 32) ? v : 8;
+  }
+  return cached;
+}
+
 }  // namespace wdgh
 
 using namespace wdgh;
@@ -133,24 +148,30 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
   const bool ranged_ok = (d % 4 == 0) && (d >= 128 || d == 64 || d == 32);
   const int64_t colw = y_host ? e2e_col_width(d) : 0;   // > 0: column-block form (Y travels back under the X copies)
   const int KC = colw ? (int)(d / colw) : 0;
-  const int K = colw ? KC : (ranged_ok ? e2e_chunks() : 1);
+  int R = colw ? e2e_col_rows() : 1;                    // row chunks per column block
+  while (R > 1 && (KC * R > 64 || R > e2e_chunks())) R /= 2;
+  const int K = colw ? R : (ranged_ok ? e2e_chunks() : 1);   // row blocks whose column segments are needed
   // 1. graph + labels first (the compute stream needs them at once) ...
   WDGH_CUDA(cudaMemcpyAsync(c.rowptr, rowptr_host, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sc));
   if (nnz) WDGH_CUDA(cudaMemcpyAsync(c.col, col_host, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
   WDGH_CUDA(cudaMemcpyAsync(c.labels, labels_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
   WDGH_CUDA(cudaEventRecord(c.ev_csr, sc));
-  // 2. ... then the feature matrix on the copy stream: column blocks (pitched) when Y goes back to the host,
-  //    row blocks otherwise
+  // 2. ... then the feature matrix on the copy stream: column blocks (pitched, each in R row chunks) when Y goes back
+  //    to the host, row blocks otherwise
   const int64_t blk = (n + K - 1) / K;
   int64_t bounds_h[65];
-  for (int k = 0; k < KC; ++k) {
-    WDGH_CUDA(cudaMemcpy2DAsync(c.x + k * colw, d * sizeof(float), x_host + k * colw, d * sizeof(float),
-                                colw * sizeof(float), n, cudaMemcpyHostToDevice, sc));
-    WDGH_CUDA(cudaEventRecord(c.ev_x[k], sc));
+  for (int k = 0; k < K; ++k) bounds_h[k] = (int64_t)k * blk < n ? (int64_t)k * blk : n;
+  for (int kc = 0; kc < KC; ++kc) {
+    for (int r = 0; r < R; ++r) {
+      const int64_t r0 = bounds_h[r], r1 = (r0 + blk < n) ? r0 + blk : n;
+      if (r1 > r0)
+        WDGH_CUDA(cudaMemcpy2DAsync(c.x + r0 * d + kc * colw, d * sizeof(float), x_host + r0 * d + kc * colw,
+                                    d * sizeof(float), colw * sizeof(float), r1 - r0, cudaMemcpyHostToDevice, sc));
+      WDGH_CUDA(cudaEventRecord(c.ev_x[kc * R + r], sc));
+    }
   }
   for (int k = 0; k < K && !colw; ++k) {
-    const int64_t r0 = (int64_t)k * blk, r1 = (r0 + blk < n) ? r0 + blk : n;
-    bounds_h[k] = r0;
+    const int64_t r0 = bounds_h[k], r1 = (r0 + blk < n) ? r0 + blk : n;
     if (r1 > r0)
       WDGH_CUDA(cudaMemcpyAsync(c.x + r0 * d, x_host + r0 * d, (size_t)(r1 - r0) * d * sizeof(float),
                                 cudaMemcpyHostToDevice, sc));
@@ -180,16 +201,35 @@ extern "C" int wdgh_pipeline_host(const int64_t *rowptr_host, const int32_t *col
                              c.match, c.labels8, n, 0, st);
   if (rc) return rc;
   if (colw) {
-    // 4'. one full-graph aggregation launch per arriving column block; its Y block leaves at once on the third stream
-    for (int k = 0; k < KC; ++k) {
-      WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[k], 0));
-      rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, c.x + k * colw, colw, d, c.y + k * colw, d, norm, add_self_loop,
-                         dinv, code, c.plan, plan_host, c.partial, 0, st);
+    // 4'. per column block: one aggregation phase per arriving row chunk (R = 1: one full-graph launch); the Y block
+    //     leaves on the third stream as soon as its last phase is done
+    if (R > 1) {
+      WDGH_CUDA(cudaMemcpyAsync(c.bounds, bounds_h, (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+      rc = wdgh_column_segments(c.rowptr, c.col, n, c.bounds, R + 1, c.seg, st);
       if (rc) return rc;
-      WDGH_CUDA(cudaEventRecord(c.ev_y[k], st));
-      WDGH_CUDA(cudaStreamWaitEvent(sb, c.ev_y[k], 0));
-      WDGH_CUDA(cudaMemcpy2DAsync(y_host + k * colw, d * sizeof(float), c.y + k * colw, d * sizeof(float),
-                                  colw * sizeof(float), n, cudaMemcpyDeviceToHost, sb));
+      rc = wdgh_plan_heavy_flags(c.plan, plan_host, n, c.skip, st);
+      if (rc) return rc;
+    }
+    for (int kc = 0; kc < KC; ++kc) {
+      const float *xb = c.x + kc * colw;
+      float *yb = c.y + kc * colw;
+      for (int r = 0; r < R; ++r) {
+        WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[kc * R + r], 0));
+        if (R == 1) {
+          rc = wdgh_spmm_csr(c.rowptr, c.col, nullptr, n, xb, colw, d, yb, d, norm, add_self_loop, dinv, code, c.plan,
+                             plan_host, c.partial, 0, st);
+        } else {
+          const int last = (r == R - 1);
+          rc = wdgh_spmm_csr_ranged(c.rowptr, c.seg + (size_t)r * n, c.seg + (size_t)(r + 1) * n, c.col, nullptr, n, xb,
+                                    colw, d, yb, d, norm, add_self_loop, dinv, code, c.skip, r > 0, last, last, nullptr,
+                                    0, 0, 0, 0, 0, c.plan, plan_host, c.partial, 0, st);
+        }
+        if (rc) return rc;
+      }
+      WDGH_CUDA(cudaEventRecord(c.ev_y[kc], st));
+      WDGH_CUDA(cudaStreamWaitEvent(sb, c.ev_y[kc], 0));
+      WDGH_CUDA(cudaMemcpy2DAsync(y_host + kc * colw, d * sizeof(float), yb, d * sizeof(float), colw * sizeof(float), n,
+                                  cudaMemcpyDeviceToHost, sb));
     }
   } else if (K == 1) {
     WDGH_CUDA(cudaStreamWaitEvent(st, c.ev_x[0], 0));

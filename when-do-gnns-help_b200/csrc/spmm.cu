@@ -329,6 +329,13 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
     nostore = __ballot_sync(kFull, !inr || hv);
     total = __shfl_sync(kFull, inc, 31);
     si = (norm != WDGH_NORM_NONE && ra.finalize && inr) ? __ldg(dinv + r + row_offset) : 1.f;
+    if (FULL && ra.accumulate && inr && !hv && (e > b || ra.finalize)) {
+      // `y +=` phase: flush_row reads the row's earlier partial sum right before it stores -- a dependent HBM round
+      // trip per row, 32 in a row per group.  Ask for the lines one group ahead so that the read is an L2 hit.
+      const float *yp = y + r * ldy;
+#pragma unroll
+      for (int c0 = 0; c0 < TILE; c0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + c0));
+    }
     __syncwarp();
   };
   // column id, weight and row slot of stream position t0 + lane of group g
