@@ -84,13 +84,16 @@ static int64_t e2e_col_width(int64_t d) {
 
 // Row chunks per column block of the Y-returning form: the block's aggregation is phased by arriving row chunk (as in
 // the counters-only form), so that only the last chunk's phase -- not a whole-graph launch -- stands between the end of
-// a block's H2D copy and the start of its D2H copy.  WDGH_E2E_COLROWS overrides (1 = one launch per column block).
+// a block's H2D copy and the start of its D2H copy.  A phase over 50M rows costs 20-23 ms at 64 columns whatever the
+// range length (tools/phase_probe.py; 52.8 ms for the whole block in one launch), so the phases of a block must fit under
+// its 230 ms H2D copy.  Measured per step: 858.9 ms (1 chunk), 831.7 ms (4), 828.9 ms (8); 4 keeps the larger margin.
+// WDGH_E2E_COLROWS overrides (1 = one launch per column block).
 static int e2e_col_rows() {
   static int cached = 0;
   if (cached == 0) {
-    int v = 8;
+    int v = 4;
     if (const char *e = getenv("WDGH_E2E_COLROWS")) v = atoi(e);
-    cached = (v >= 1 && v <= 32) ? v : 8;
+    cached = (v >= 1 && v <= 32) ? v : 4;
   }
   return cached;
 }

@@ -274,7 +274,10 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
                      int64_t row_offset, RangeArgs ra, unsigned long long *__restrict__ sched) {
   constexpr int TILE = 32 * VEC * NCH;
   constexpr int U0 = 32 / (VEC * NCH);
-  constexpr int U = U0 > 16 ? 16 : (U0 < 2 ? 2 : U0);
+  // gather batch: feature rows in flight per lane.  Capped at 8: with 16 (the natural value for 64 / 32 columns) the
+  // 64-column kernel ran the full graph in 76.3 ms and a short-range phase in 55-65 ms; with 8 it takes 52.8 ms and
+  // 20-21 ms (tools/phase_probe.py, profiles/phase_probe_r02.txt)
+  constexpr int U = U0 > 8 ? 8 : (U0 < 2 ? 2 : U0);
   constexpr unsigned kFull = 0xffffffffu;
   __shared__ float table[256];
   __shared__ int s_off[2][33];      // stream offset of every row slot of the group (exclusive scan), [32] = total
@@ -331,7 +334,8 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
     si = (norm != WDGH_NORM_NONE && ra.finalize && inr) ? __ldg(dinv + r + row_offset) : 1.f;
     if (FULL && ra.accumulate && inr && !hv && (e > b || ra.finalize)) {
       // `y +=` phase: flush_row reads the row's earlier partial sum right before it stores -- a dependent HBM round
-      // trip per row, 32 in a row per group.  Ask for the lines one group ahead so that the read is an L2 hit.
+      // trip per row, 32 in a row per group.  Ask for the lines one group ahead so that the read is an L2 hit
+      // (measured on the 16-phase e2e schedule at 64 columns: 59 -> 56 ms per phase).
       const float *yp = y + r * ldy;
 #pragma unroll
       for (int c0 = 0; c0 < TILE; c0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + c0));
