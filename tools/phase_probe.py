@@ -21,6 +21,9 @@ from wdgh_b200 import graph as G  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nodes", type=int, default=50_000_000)
+    ap.add_argument("--widths", type=int, nargs="+", default=[128, 64])
+    ap.add_argument("--chunks", type=int, nargs="+", default=[1, 2, 4, 8, 16])
+    ap.add_argument("--reps", type=int, default=2)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     n, d = a.nodes, 128
@@ -30,13 +33,13 @@ def main():
     dinv, _, code = g.degree_scale(W.NORM_SYM, True)
     skip = G.heavy_flags(g) if g.n_chunks else None
     y = torch.empty_like(x)
-    for w in (128, 64):
+    for w in a.widths:
         xv, yv = x[:, :w], y[:, :w]
-        for R in (1, 2, 4, 8, 16):
+        for R in a.chunks:
             blk = (n + R - 1) // R
             seg = G.column_segments(g, [min(r * blk, n) for r in range(R)] + [n])
             times = []
-            for rep in range(2):
+            for rep in range(a.reps):
                 evs = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
                 evs[0].record()
                 for r in range(R):
