@@ -155,3 +155,33 @@ def test_bench_reference_arm_contract():
     assert line["config"]["nodes"] == 20000
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=root, env={**os.environ, "RANK": "1"})
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_similarity_near_ties_counts_exact_ties():
+    """oracle.similarity_near_ties (the sweep's tolerance for soft LAS): a node whose aggregated label distribution is
+    uniform has ratio = 1 in exact arithmetic whatever the class sizes are -- those nodes, and only those, are counted."""
+    from oracle import ref_port as O
+    c, per = 4, 6
+    n = c * per
+    labels = np.repeat(np.arange(c), per)
+    # ring inside every class (strongly homophilous: ratio > 1 for everybody) ...
+    src = np.arange(n)
+    dst = (src // per) * per + (src % per + 1) % per
+    row, col = np.concatenate([src, dst]), np.concatenate([dst, src])
+    oh = np.eye(c, dtype=np.float32)[labels]
+
+    def rownorm(row, col):
+        a = np.zeros((n, n))
+        a[row, col] = 1.0
+        a = a / a.sum(1, keepdims=True)
+        r, c_ = np.nonzero(a)
+        return r, c_, a[r, c_]
+    r, c_, v = rownorm(row, col)
+    assert O.similarity_near_ties(oh, r, c_, v, n, oh) == 0
+    # ... then node 0 is rewired to exactly one neighbour of every class: its row of A X is uniform -> an exact tie
+    keep = (row != 0) & (col != 0)
+    extra_dst = np.array([1, per, 2 * per, 3 * per])
+    row2 = np.concatenate([row[keep], np.zeros(4, np.int64)])
+    col2 = np.concatenate([col[keep], extra_dst])
+    r, c_, v = rownorm(row2, col2)
+    assert O.similarity_near_ties(oh, r, c_, v, n, oh) == 1
