@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--widths", type=int, nargs="+", default=[128, 64])
     ap.add_argument("--chunks", type=int, nargs="+", default=[1, 2, 4, 8, 16])
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--ctas", type=int, nargs="+", default=[0], help="CTAs per SM of the ranged launches (0 = default 32)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     n, d = a.nodes, 128
@@ -35,7 +36,7 @@ def main():
     y = torch.empty_like(x)
     for w in a.widths:
         xv, yv = x[:, :w], y[:, :w]
-        for R in a.chunks:
+        for R, ctas in [(R, c) for R in a.chunks for c in a.ctas]:
             blk = (n + R - 1) // R
             seg = G.column_segments(g, [min(r * blk, n) for r in range(R)] + [n])
             times = []
@@ -45,11 +46,11 @@ def main():
                 for r in range(R):
                     last = r == R - 1
                     G.spmm_ranged(g, seg[r], seg[r + 1], xv, yv, W.NORM_SYM, True, dinv, code, skip, accumulate=r > 0,
-                                  finalize=last, run_split_rows=last)
+                                  finalize=last, run_split_rows=last, ctas_per_sm=ctas)
                     evs[r + 1].record()
                 torch.cuda.synchronize()
                 times = [evs[r].elapsed_time(evs[r + 1]) for r in range(R)]
-            print(f"width {w:3d}  R={R:2d}: total {sum(times):8.2f} ms   per phase " + " ".join(f"{t:6.1f}" for t in times), flush=True)
+            print(f"width {w:3d}  R={R:2d} ctas/SM={ctas or 32:2d}: total {sum(times):8.2f} ms   per phase " + " ".join(f"{t:6.1f}" for t in times), flush=True)
 
 
 if __name__ == "__main__":
