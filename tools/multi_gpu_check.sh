@@ -1,6 +1,6 @@
-# usage: bash tools/_multi_final.sh N [check]  -- final-code bench (default settings, traced stages) at world size N, optional partition check
+# usage (on an N-GPU box): bash tools/multi_gpu_check.sh N [check]  -- final-code bench (default settings, traced stages) at world size N, optional partition check
 N=$1
-cd $GRAFT_REPO_ROOT
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 if [ "$2" = "check" ]; then
 timeout 900 $TR --nproc-per-node $N --master-port 29541 tools/check_partitions.py --nodes 1000003 2000000 > gpurun_out/r9_check_n$N.log 2>&1; echo "check n$N rc=$?"; grep '"check"' gpurun_out/r9_check_n$N.log | tail -1 | cut -c1-900
