@@ -447,7 +447,6 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
 
   while (true) {
     int cur = 0;
-    bool next_ready = false;
     auto prefetch = [&](int t0, bool last_seg) {
       if (!last_seg) {
         load_seg(buf, g, t0 + 32, total, nj, nw, nrho);
@@ -456,23 +455,42 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         load_seg(buf ^ 1, gn, 0, n_total, nj, nw, nrho);
         gnn = take(gn);
         load_bounds(gnn, b, e, flag);
-        next_ready = true;
       }
     };
-    for (int t0 = 0; t0 < total; t0 += 32) {
+    // (a group without entries still makes one pass with cnt = 0: every gather predicated off, nothing consumed -- it
+    // is what fetches the next group, so that the prefetch code exists once)
+    for (int t0 = 0; t0 < total || t0 == 0; t0 += 32) {
       const int cnt = min(32, total - t0);
       const bool last_seg = t0 + 32 >= total;
       bool next_issued = false;
-      int k = 0;
-      for (; k + U <= cnt; k += U) {  // full batches: U unpredicated gathers in flight
+      // One batch loop: the gathers come in two flavours -- every batch but the last of a segment is full and issues
+      // U unpredicated loads -- but the prefetch of the next segment / group and the consuming side (row flush + fma)
+      // exist ONCE.  (They used to be duplicated for the predicated last batch: the kernel was 4096 SASS instructions,
+      // and a launch over short row ranges, which runs the whole body once per group, was instruction-fetch bound:
+      // 78% of its stall samples, profiles/summary_r02.md.)
+#pragma unroll 1
+      for (int k = 0; k < cnt || k == 0; k += U) {
         Vec<VEC> v[U][NCH];
+        if (k + U <= cnt) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float *xr = row_ptr(__shfl_sync(kFull, j, k + u));
+          for (int u = 0; u < U; ++u) {
+            const float *xr = row_ptr(__shfl_sync(kFull, j, k + u));
 #pragma unroll
-          for (int t = 0; t < NCH; ++t) {
-            if (live[t]) v[u][t].load(xr + t * (32 * VEC));
-            else v[u][t].zero();
+            for (int t = 0; t < NCH; ++t) {
+              if (live[t]) v[u][t].load(xr + t * (32 * VEC));
+              else v[u][t].zero();
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool on = k + u < cnt;
+            const float *xr = row_ptr(__shfl_sync(kFull, j, on ? k + u : 0));
+#pragma unroll
+            for (int t = 0; t < NCH; ++t) {
+              if (on && live[t]) v[u][t].load(xr + t * (32 * VEC));
+              else v[u][t].zero();
+            }
           }
         }
         if (!next_issued) {
@@ -481,32 +499,7 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int ru = __shfl_sync(kFull, rho, k + u);
-          while (cur < ru) flush_row(cur++);
-          const float wu = __shfl_sync(kFull, w, k + u);
-#pragma unroll
-          for (int t = 0; t < NCH; ++t) acc[t].fma(wu, v[u][t]);
-        }
-      }
-      if (k < cnt) {  // last batch of the group, predicated
-        Vec<VEC> v[U][NCH];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool on = k + u < cnt;
-          const float *xr = row_ptr(__shfl_sync(kFull, j, on ? k + u : 0));
-#pragma unroll
-          for (int t = 0; t < NCH; ++t) {
-            if (on && live[t]) v[u][t].load(xr + t * (32 * VEC));
-            else v[u][t].zero();
-          }
-        }
-        if (!next_issued) {
-          prefetch(t0, last_seg);
-          next_issued = true;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (k + u < cnt) {
+          if (k + u < cnt) {  // warp-uniform
             const int ru = __shfl_sync(kFull, rho, k + u);
             while (cur < ru) flush_row(cur++);
             const float wu = __shfl_sync(kFull, w, k + u);
@@ -515,10 +508,6 @@ spmm_rowgroup_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
           }
         }
       }
-      j = nj; w = nw; rho = nrho;
-    }
-    if (!next_ready) {  // a group without entries
-      prefetch(0, true);
       j = nj; w = nw; rho = nrho;
     }
     while (cur < 32) flush_row(cur++);
