@@ -722,8 +722,34 @@ def main():
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
     e2e = None
+    stage_ms = getattr(pipe, "stage_ms", None)
     if not args.no_e2e:
-        e2e = run_e2e(args, W, G, world, rank, device, g, x_local, labels_local, nnz, part)
+        if world > 1:
+            # The e2e arm builds its own (1-D, host-staged) pipeline with a second peer-mapped feature buffer.  Release
+            # everything the device-resident part allocated first -- the 2-D pipeline alone holds the full-size
+            # x_full (25.6 GB on every rank) and the receive slots -- and agree COLLECTIVELY whether the rest fits: a rank
+            # that ran out of memory alone would leave its peers hanging in a collective.
+            import gc
+            pipe = slice_graphs = y_last = None
+            xs = ys = dinv = code = None
+            if use_2d:
+                x_cols = out_slice = dinv_f = code_f = dinv2 = code2 = None
+            gc.collect()
+            torch.cuda.empty_cache()
+            free_b, _ = torch.cuda.mem_get_info(device)
+            rows_l = r1 - r0
+            need = (part.padded * d * 4                      # the e2e pipeline's peer-mapped feature buffer
+                    + 3 * rows_l * d * 4                      # staged features, Y, and slack for scratch
+                    + (world + 2) * rows_l * 8                # column segments per source rank
+                    + 3 * (int(g.rowptr.numel()) * 8 + int(g.col.numel()) * 4))
+            ok = torch.tensor([1 if free_b >= 1.15 * need else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": f"skipped: {free_b / 1e9:.0f} GB free on rank {rank} after releasing the device-resident "
+                               f"pipeline, the host-staged pipeline needs ~{need / 1e9:.0f} GB"}
+        if e2e is None:
+            e2e = run_e2e(args, W, G, world, rank, device, g, x_local, labels_local, nnz, part)
 
     # ---- secondary rooflines (N = 1): the label pass (HBM) and the tcgen05 Gram (tensor pipe) -------
     roofline_labels = roofline_gram = None
@@ -755,7 +781,7 @@ def main():
                 "roofline": roofline, "roofline_labels": roofline_labels, "roofline_gram": roofline_gram,
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "metrics": metrics, "verify": verify, "nvlink": nvlink,
-                "stage_ms": getattr(pipe, "stage_ms", None)}
+                "stage_ms": stage_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
