@@ -387,11 +387,12 @@ def linkx_kr_check(hm, row, col, labels, features, n, device, epochs=3):
             continue
         for side, kname in (("pred_g", "gram_g"), ("pred_x", "gram_x")):
             changed = got[side].cpu() != ref[side]
-            unstable = O.kr_unstable_nodes(ref[kname], ref["n_layers"], ref["tr"], ref["va"], ref["onehot_tr"])
+            outside, unstable, _ = O.kr_flips_outside_unstable(changed, ref[kname], ref["n_layers"], ref["tr"], ref["va"],
+                                                               ref["onehot_tr"])
             out["predictions"] += int(changed.numel())
             out["flips"] += int(changed.sum())
             out["unstable_predictions"] += int(unstable.sum())
-            out["flips_outside_unstable"] += int((changed & ~unstable).sum())
+            out["flips_outside_unstable"] += outside
     out["ok"] = out["flips_outside_unstable"] == 0
     return out
 

@@ -174,8 +174,9 @@ def kr_contract(clf, p, trace, ref_trace, gold_p, gold_acc_g, gold_acc_x):
             if clf == "gnb":
                 assert int(changed.sum()) <= 1, (clf, e, side)
                 continue
-            unstable = O.kr_unstable_nodes(ref[kname], ref["n_layers"], ref["tr"], ref["va"], ref["onehot_tr"])
-            assert not bool((changed & ~unstable).any()), (clf, e, side, int(changed.sum()), int(unstable.sum()))
+            outside, unstable, _ = O.kr_flips_outside_unstable(changed, ref[kname], ref["n_layers"], ref["tr"], ref["va"],
+                                                               ref["onehot_tr"])
+            assert outside == 0, (clf, e, side, int(changed.sum()), int(unstable.sum()))
             # a well-conditioned epoch flips at most a few near-ties; an epoch the oracle flags as noise-decided as a
             # whole (rank-deficient train Gram under pinv(rcond=1e-15): >= 90% of the nodes unstable) is unconstrained
             assert int(changed.sum()) <= max(1, n_val // 20) or int(unstable.sum()) * 10 >= 9 * n_val, \

@@ -151,9 +151,10 @@ def compare(O, key, n, got, traces, ref, ref_traces, near, worst, kr, bad):
                 changed = g_[side].cpu() != r_[side]
                 if bool(changed.any()):
                     same = False
-                    unstable = O.kr_unstable_nodes(r_[kname], r_["n_layers"], r_["tr"], r_["va"], r_["onehot_tr"])
+                    outside, _, n_esc = O.kr_flips_outside_unstable(changed, r_[kname], r_["n_layers"], r_["tr"], r_["va"],
+                                                                    r_["onehot_tr"])
                     kr["flips"] += int(changed.sum())
-                    outside = int((changed & ~unstable).sum())
+                    kr["escalated_analyses"] = kr.get("escalated_analyses", 0) + n_esc
                     kr["flips_outside_unstable"] += outside
                     if outside:
                         bad.append((key, clf, side, e, outside))
