@@ -142,6 +142,9 @@ def test_kr_p_value_is_decided_by_rounding_noise(name, monkeypatch):
         changed = a["pred_g"] != b["pred_g"]
         flips += int(changed.sum())
         assert not bool((changed & ~unstable).any())
+        # the helper the GPU tests / the sweep use: same set, nothing outside it, no denser re-draw needed here
+        outside, used, escalations = O.kr_flips_outside_unstable(changed, a["gram_g"], 1, a["tr"], a["va"], a["onehot_tr"])
+        assert outside == 0 and escalations == 0 and torch.equal(used, unstable)
         assert torch.equal(a["pred_x"], b["pred_x"]) or bool(
             O.kr_unstable_nodes(a["gram_x"], 1, a["tr"], a["va"], a["onehot_tr"])[a["pred_x"] != b["pred_x"]].all())
     assert flips >= 1
